@@ -1,0 +1,92 @@
+"""ctypes binding of ``libgss.so`` (the C ABI declared in ``include/gss_api.h``).
+
+There is NO fallback: if the shared library is missing, or a call returns a
+non-zero status, this module raises.  The CPU oracle under ``oracle/`` is test
+infrastructure and is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgss.so")
+
+GSS_OK, GSS_EINVAL, GSS_EUNSUPPORTED, GSS_ECUDA, GSS_ENOMEM = 0, -1, -2, -3, -4
+FLAG_LOG, FLAG_EXP = 1, 2
+
+# name -> (restype, argtypes); mirrors include/gss_api.h one to one
+_P = c_void_p
+SIGNATURES = {
+    "gss_version": (c_int, []),
+    "gss_last_error": (c_char_p, []),
+    "gss_launch_count": (c_int64, []),
+    "gss_supported_fft_sizes": (c_int, [POINTER(c_int), c_int]),
+    "gss_frame_count": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
+    "gss_stft_packed": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P]),
+    "gss_stft_packed_i16": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P]),
+    "gss_istft_packed": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int64, _P]),
+    "gss_mask_istft": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, _P, c_int64, _P]),
+    "gss_apply_mask": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P]),
+    "gss_to_log": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
+    "gss_to_exp": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
+    "gss_cross_snr": (c_int, [_P, _P, c_int64, c_int, c_int, c_int64, c_float, _P, _P]),
+    "gss_ae_partial": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P]),
+    "gss_wav16_normalise": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "gss_stft_packed_host": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P]),
+    "gss_istft_packed_host": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P]),
+    "gss_stft_h2d": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int, _P]),
+    "gss_mask_istft_d2h": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, _P, _P, c_int64, c_int, _P]),
+}
+
+_lib = None
+
+
+class GssError(RuntimeError):
+    """A libgss call failed with GSS_ECUDA / GSS_ENOMEM."""
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m gan_sass_tf_b200.build` "
+                "(nvcc, sm_100a).  There is no CPU fallback.")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)          # AttributeError if the ABI and this table disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc: int):
+    """0 -> None; GSS_EINVAL/GSS_EUNSUPPORTED -> ValueError (what the reference's
+    asserts / SciPy raise for bad shapes); anything else -> GssError."""
+    if rc == GSS_OK:
+        return
+    msg = lib().gss_last_error().decode("utf-8", "replace")
+    if rc in (GSS_EINVAL, GSS_EUNSUPPORTED):
+        raise ValueError(f"libgss: {msg}")
+    raise GssError(f"libgss ({rc}): {msg}")
+
+
+def frame_count(n: int, N: int, H: int):
+    """(T, nadd) of ``scipy.signal.stft(boundary='zeros', padded=True)`` (main.py:97)."""
+    T, nadd = c_int64(0), c_int64(0)
+    check(lib().gss_frame_count(n, N, H, ctypes.byref(T), ctypes.byref(nadd)))
+    return T.value, nadd.value
+
+
+def supported_fft_sizes():
+    buf = (c_int * 16)()
+    k = lib().gss_supported_fft_sizes(buf, 16)
+    return tuple(buf[i] for i in range(min(k, 16)))
+
+
+def launch_count() -> int:
+    return int(lib().gss_launch_count())

@@ -1,0 +1,215 @@
+"""Spectral ops on CUDA tensors - the drop-in for the reference's ``app/ops.py``.
+
+Same style as the reference: free functions, tensor in / tensor out, last axis =
+``hparams.FFT_SIZE`` read at call time, any leading rank, shape errors by
+``assert`` (ops.py:26-31, :176, :205-206).  Kept names / argument order:
+``to_log_signal`` (ops.py:228-238), ``to_exp_signal`` (:241-251), ``batch_snr``
+(:162-189), ``batch_cross_snr`` (:191-225).  New ops replace the host-side SciPy
+calls: ``stft`` / ``stft_log`` (main.py:97-98 + :338), ``istft`` (main.py:110-111),
+``apply_mask`` and the fused ``mask_istft``.
+
+Every function enqueues hand-written sm_100a kernels (``csrc/``) on the current
+torch CUDA stream through the C ABI; PyTorch only owns the buffers.  CPU tensors
+are rejected - there is no fallback path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import hparams
+from .. import _native as _n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: tensor is on {t.device}; gan_sass_tf_b200 ops run on CUDA only (no CPU fallback)")
+    return t
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _dev(t, name)
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
+def _nh(fft_size, hop):
+    """(N, H): explicit arguments win; else ``hparams.FFT_SIZE`` and, for that size,
+    ``hparams.hop_size()``; any other size defaults to SciPy's ``N // 2``."""
+    N = hparams.FFT_SIZE if fft_size is None else int(fft_size)
+    if hop is not None:
+        return N, int(hop)
+    return N, (hparams.hop_size() if N == hparams.FFT_SIZE else N // 2)
+
+
+# ---------------------------------------------------------------------------
+# transforms
+# ---------------------------------------------------------------------------
+def stft(wave, fft_size=None, hop=None, log=False):
+    """``scipy.signal.stft(x, nperseg=N)[2]`` + ``utils.spectrum_to_feature``
+    (main.py:97-98) for a batch: ``wave [..., n]`` (float32 or int16) ->
+    packed feature ``[..., T, N]`` float32.  ``log=True`` fuses ``to_log_signal``."""
+    _dev(wave, "stft")
+    N, H = _nh(fft_size, hop)
+    if wave.dtype == torch.int16:
+        w, fn = wave.contiguous(), _n.lib().gss_stft_packed_i16
+    else:
+        w, fn = _f32c(wave, "stft"), _n.lib().gss_stft_packed
+    lead, n = w.shape[:-1], w.shape[-1]
+    assert n >= 1, "stft: empty waveform"
+    T, _ = _n.frame_count(n, N, H)
+    B = 1
+    for d in lead:
+        B *= d
+    feat = torch.empty(lead + (T, N), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _n.check(fn(w.data_ptr(), B, n, n, N, H, _n.FLAG_LOG if log else 0, hparams.EPS, feat.data_ptr(), _stream()))
+    return feat
+
+
+def stft_log(wave, fft_size=None, hop=None):
+    """STFT with ``to_log_signal`` fused into the epilogue: what the separator consumes (main.py:338)."""
+    return stft(wave, fft_size, hop, log=True)
+
+
+def istft(feature, hop=None, length=None, exp=False):
+    """``utils.feature_to_spectrum`` + ``scipy.signal.istft(Z, nperseg=N)``
+    (main.py:110-111): ``feature [..., T, N]`` -> ``[..., (T-1)*H]``.  ``exp=True``
+    applies ``to_exp_signal`` first (main.py:342).  ``length`` trims the tail
+    (SciPy itself returns the ``nadd`` padding samples, K4)."""
+    f = _f32c(feature, "istft")
+    assert f.dim() >= 2, "istft: feature must be [..., T, N]"
+    T, N = f.shape[-2], f.shape[-1]
+    N, H = _nh(N, hop)
+    lead = f.shape[:-2]
+    R = 1
+    for d in lead:
+        R *= d
+    L = (T - 1) * H
+    out = torch.empty(lead + (L,), dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        _n.check(_n.lib().gss_istft_packed(f.data_ptr(), R, T, N, H, _n.FLAG_EXP if exp else 0, hparams.EPS,
+                                           out.data_ptr(), L, _stream()))
+    return out if length is None else out[..., :length]
+
+
+def apply_mask(mix_feature, mask):
+    """``mix_feature [B,T,N]``, ``mask [B,S,T,N/2]`` -> ``[B*S,T,N]``: one real gain per
+    complex bin (both packed halves; slot 0 = DC+Nyquist share a gain, the pairing
+    of ops.py:234-237), output row ``b*S+s`` (modules.py:396-399)."""
+    x = _f32c(mix_feature, "apply_mask")
+    m = _f32c(mask, "apply_mask")
+    assert x.dim() == 3 and m.dim() == 4, "apply_mask: mix [B,T,N], mask [B,S,T,N/2]"
+    B, T, N = x.shape
+    S = m.shape[1]
+    assert m.shape == (B, S, T, N // 2), f"apply_mask: mask shape {tuple(m.shape)} != {(B, S, T, N // 2)}"
+    out = torch.empty((B * S, T, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _n.check(_n.lib().gss_apply_mask(x.data_ptr(), m.data_ptr(), B, S, T, N, out.data_ptr(), _stream()))
+    return out
+
+
+def mask_istft(wave, mask, fft_size=None, hop=None, out=None):
+    """Fused synthesis: STFT of the mixture (recomputed from ``wave [B,n]``), per-source
+    mask ``[B,S,T,N/2]``, inverse STFT with overlap-add -> ``[B*S, (T-1)*H]``."""
+    w = _f32c(wave, "mask_istft")
+    m = _f32c(mask, "mask_istft")
+    assert w.dim() == 2 and m.dim() == 4, "mask_istft: wave [B,n], mask [B,S,T,N/2]"
+    N, H = _nh(fft_size if fft_size is not None else 2 * m.shape[-1], hop)
+    B, n = w.shape
+    S = m.shape[1]
+    T, _ = _n.frame_count(n, N, H)
+    assert m.shape == (B, S, T, N // 2), f"mask_istft: mask shape {tuple(m.shape)} != {(B, S, T, N // 2)}"
+    L = (T - 1) * H
+    if out is None:
+        out = torch.empty((B * S, L), dtype=torch.float32, device=w.device)
+    else:
+        assert out.is_cuda and out.dtype == torch.float32 and out.shape == (B * S, L) and out.is_contiguous()
+    with torch.cuda.device(w.device):
+        _n.check(_n.lib().gss_mask_istft(w.data_ptr(), m.data_ptr(), B, S, n, n, N, H, out.data_ptr(), L, _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# element-wise compression (reference names)
+# ---------------------------------------------------------------------------
+def _logexp(s_signal, fn_name):
+    x = _f32c(s_signal, fn_name)
+    N = hparams.FFT_SIZE
+    assert x.shape[-1] == N, f"{fn_name}: last axis {x.shape[-1]} != FFT_SIZE {N}"
+    out = torch.empty_like(x)
+    rows = x.numel() // N
+    with torch.cuda.device(x.device):
+        _n.check(getattr(_n.lib(), fn_name)(x.data_ptr(), out.data_ptr(), rows, N, hparams.EPS, _stream()))
+    return out
+
+
+def to_log_signal(s_signal):
+    """ops.py:228-238: each bin pair ``(k, k+N/2)`` scaled by ``0.5*log1p(a2)*rsqrt(a2+EPS)``."""
+    return _logexp(s_signal, "gss_to_log")
+
+
+def to_exp_signal(s_signal):
+    """ops.py:241-251: ``a = sqrt(re^2+im^2+EPS)``, scale ``expm1(a)/a`` (not the inverse of to_log, K7)."""
+    return _logexp(s_signal, "gss_to_exp")
+
+
+# ---------------------------------------------------------------------------
+# metrics (reference names)
+# ---------------------------------------------------------------------------
+def batch_cross_snr(clear_signal, noisy_signal):
+    """ops.py:191-225: ``[B,m,...]`` x ``[B,n,...]`` -> ``[B,m,n]``."""
+    c = _f32c(clear_signal, "batch_cross_snr")
+    z = _f32c(noisy_signal, "batch_cross_snr")
+    assert c.dim() == z.dim()
+    assert c.dim() >= 2
+    assert c.shape[0] == z.shape[0] and c.shape[2:] == z.shape[2:], "batch_cross_snr: trailing shapes differ"
+    B, m, n = c.shape[0], c.shape[1], z.shape[1]
+    L = 1
+    for d in c.shape[2:]:
+        L *= d
+    out = torch.empty((B, m, n), dtype=torch.float32, device=c.device)
+    with torch.cuda.device(c.device):
+        _n.check(_n.lib().gss_cross_snr(c.data_ptr(), z.data_ptr(), B, m, n, L, hparams.EPS, out.data_ptr(), _stream()))
+    return out
+
+
+def batch_snr(clear_signal, noisy_signal):
+    """ops.py:162-189: ``[B,...]`` x ``[B,...]`` -> ``[B]`` (the m = n = 1 case of the cross SNR)."""
+    c = _dev(clear_signal, "batch_snr")
+    z = _dev(noisy_signal, "batch_snr")
+    assert c.dim() == z.dim()
+    assert c.shape == z.shape, "batch_snr: shapes differ"
+    B = c.shape[0]
+    return batch_cross_snr(c.reshape(B, 1, -1), z.reshape(B, 1, -1)).reshape(B)
+
+
+def ae_loss(separated, mixed, n_out):
+    """main.py:353-361: ``mean((sum_s sep[b,s] - mix[b])^2)`` with ``separated [B*S,T,N]``."""
+    s = _f32c(separated, "ae_loss")
+    x = _f32c(mixed, "ae_loss")
+    B = x.shape[0]
+    assert s.shape[0] == B * n_out and s.shape[1:] == x.shape[1:]
+    L = x.numel() // B
+    part = torch.empty((B,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _n.check(_n.lib().gss_ae_partial(s.data_ptr(), x.data_ptr(), B, n_out, L, part.data_ptr(), _stream()))
+    return part.sum() / (B * L)
+
+
+def wav16_normalise(wave):
+    """main.py:112-116: per clip shift to min, scale to 32767, truncate -> int16 ``[R, len]``."""
+    x = _f32c(wave, "wav16_normalise")
+    x2 = x.reshape(-1, x.shape[-1])
+    R, n = x2.shape
+    mm = torch.empty((R, 2), dtype=torch.float32, device=x.device)
+    pcm = torch.empty((R, n), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _n.check(_n.lib().gss_wav16_normalise(x2.data_ptr(), R, n, n, mm.data_ptr(), pcm.data_ptr(), _stream()))
+    return pcm.reshape(x.shape)

@@ -1,0 +1,396 @@
+// gss_api.cu - the C ABI of libgss (include/gss_api.h): argument checks, launch
+// planning and kernel dispatch.  No torch types, no allocation on the device
+// entry points, all work is enqueued on the caller's stream.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <cuda_runtime.h>
+
+#include "../../include/gss_api.h"
+#include "gss_elem.cuh"
+#include "gss_stream.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(GSS_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+int after_launch(const char* name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return GSS_OK;
+}
+
+int sm_count() {
+    static int sms[64]; static std::once_flag once;
+    std::call_once(once, [] { for (int& s : sms) s = 0; });
+    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); sms[dev] = v; }
+    return sms[dev];
+}
+
+bool supported_n(int N) { return N == 512; }
+
+int check_nh(int N, int H, int* hs) {
+    if (N < 16 || (N & (N - 1))) return fail(GSS_EUNSUPPORTED, "FFT_SIZE %d is not a power of two", N);
+    if (!supported_n(N)) return fail(GSS_EUNSUPPORTED, "FFT_SIZE %d not supported by this build (512)", N);
+    if (H * 2 == N) *hs = 4; else if (H * 4 == N) *hs = 2; else if (H * 8 == N) *hs = 1;
+    else return fail(GSS_EUNSUPPORTED, "hop %d must be N/2, N/4 or N/8 (N=%d)", H, N);
+    return GSS_OK;
+}
+
+int frame_count(int64_t n, int N, int H, int64_t* T, int64_t* nadd) {
+    if (n < 1 || N < 2 || H < 1 || H > N) return fail(GSS_EINVAL, "frame_count: bad (n=%lld, N=%d, H=%d)", (long long)n, N, H);
+    int64_t a = ((H - n % H) % H) % N;
+    if (nadd) *nadd = a;
+    if (T) *T = (n + a) / H + 1;
+    return GSS_OK;
+}
+
+// Choose how many frame pairs one team walks.  `rows` independent streams of
+// `npairs` pairs; each chunk recomputes `halo` pairs and pays ~2 pairs of set-up.
+// cost = waves over the resident team slots x pairs walked per team.
+gss::ChunkPlan plan_chunks(int64_t rows, int npairs, int halo, int64_t slots) {
+    gss::ChunkPlan best{npairs, 1};
+    double best_cost = 1e300;
+    for (int ppc = 1; ppc <= npairs; ++ppc) {
+        int nchunk = (npairs + ppc - 1) / ppc;
+        int64_t items = rows * nchunk;
+        int64_t waves = (items + slots - 1) / slots;
+        double cost = (double)waves * (ppc + (nchunk > 1 ? halo : 0) + 2.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = gss::ChunkPlan{ppc, nchunk}; }
+    }
+    return best;
+}
+
+template <typename K>
+int64_t team_slots(K kernel, int warps, size_t smem) {
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, warps * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+    return (int64_t)sm_count() * nb * warps;
+}
+
+constexpr int WARPS = 4;
+
+template <int N>
+size_t team_smem(int warps) { return sizeof(float) * (4 * gss::Geo<N>::TW1_F4 + (size_t)warps * gss::Geo<N>::TEAM_FLOATS); }
+
+template <typename K>
+int prep(K kernel, size_t smem) {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return GSS_OK;
+}
+
+// ---- STFT ---------------------------------------------------------------
+template <int N, int HS, bool LOG, typename TIn>
+int launch_stft(gss::StftArgs<TIn> a, cudaStream_t st) {
+    auto k = gss::stft_kernel<N, HS, LOG, TIn, WARPS>;
+    const size_t smem = team_smem<N>(WARPS);
+    if (int rc = prep(k, smem)) return rc;
+    gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, team_slots(k, WARPS, smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    int64_t items = a.B * a.nchunk;
+    k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
+    return after_launch("stft_kernel");
+}
+template <typename TIn>
+int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps, float* feat, void* stream) {
+    int hs = 0;
+    if (int rc = check_nh(N, H, &hs)) return rc;
+    if (!wave || !feat) return fail(GSS_EINVAL, "stft: null pointer");
+    if (B < 0 || n < 1 || ld < n) return fail(GSS_EINVAL, "stft: bad shape B=%lld n=%lld ld=%lld", (long long)B, (long long)n, (long long)ld);
+    if (n < N) return fail(GSS_EUNSUPPORTED, "stft: n=%lld < FFT_SIZE=%d (SciPy would silently shrink nperseg)", (long long)n, N);
+    if (flags & ~GSS_FLAG_LOG) return fail(GSS_EINVAL, "stft: unknown flags 0x%x", flags);
+    if (B == 0) return GSS_OK;
+    gss::StftArgs<TIn> a{};
+    a.wave = wave; a.feat = feat; a.B = B; a.n = n; a.ld = ld; a.eps = eps;
+    if (int rc = frame_count(n, N, H, &a.T, nullptr)) return rc;
+    a.npairs = (int)((a.T + 1) / 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool lg = flags & GSS_FLAG_LOG;
+#define GSS_CASE(NN, HH) if (N == NN && hs == HH) return lg ? launch_stft<NN, HH, true, TIn>(a, st) : launch_stft<NN, HH, false, TIn>(a, st);
+    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
+#undef GSS_CASE
+    return fail(GSS_EUNSUPPORTED, "stft: no kernel for N=%d H=%d", N, H);
+}
+
+// ---- iSTFT --------------------------------------------------------------
+template <int N, int HS, bool EXP>
+int launch_istft(gss::IstftArgs a, cudaStream_t st) {
+    auto k = gss::istft_kernel<N, HS, EXP, WARPS>;
+    const size_t smem = team_smem<N>(WARPS);
+    if (int rc = prep(k, smem)) return rc;
+    gss::ChunkPlan pl = plan_chunks(a.rows, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    int64_t items = a.rows * a.nchunk;
+    k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
+    return after_launch("istft_kernel");
+}
+
+// ---- fused synthesis ------------------------------------------------------
+template <int N, int HS, int ST>
+int launch_synth(gss::SynthArgs a, cudaStream_t st) {
+    auto k = gss::mask_istft_kernel<N, HS, ST, WARPS>;
+    const size_t smem = team_smem<N>(WARPS);
+    if (int rc = prep(k, smem)) return rc;
+    a.ngroups = (a.S + ST - 1) / ST;
+    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    int64_t items = a.B * a.ngroups * a.nchunk;
+    k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
+    return after_launch("mask_istft_kernel");
+}
+template <int N, int HS>
+int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
+    // sources carried per pass: 3 when S is a multiple of 3, else 2 (S even) or 1
+    if (a.S % 3 == 0) return launch_synth<N, HS, 3>(a, st);
+    if (a.S % 2 == 0) return launch_synth<N, HS, 2>(a, st);
+    if (a.S == 1) return launch_synth<N, HS, 1>(a, st);
+    return launch_synth<N, HS, 3>(a, st);
+}
+
+int grid_for(int64_t work_items, int block) {
+    int64_t want = (work_items + block - 1) / block;
+    int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+// grow-only device workspace for the *_host entry points
+struct Workspace {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return GSS_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { p = nullptr; return fail(GSS_ENOMEM, "workspace cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+        cap = bytes; return GSS_OK;
+    }
+};
+std::mutex g_ws_mu;
+Workspace g_ws_in, g_ws_out;
+
+struct CopyStreams {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev[8] = {};
+    bool ok = false;
+    int init() {
+        if (ok) return GSS_OK;
+        CK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ok = true; return GSS_OK;
+    }
+};
+thread_local CopyStreams g_cs;
+
+}  // namespace
+
+extern "C" {
+
+int gss_version(void) { return 100; }
+const char* gss_last_error(void) { return g_err.c_str(); }
+int64_t gss_launch_count(void) { return g_launches.load(); }
+int gss_supported_fft_sizes(int* sizes, int cap) {
+    int k = 0;
+    for (int N = 16; N <= 65536; N *= 2)
+        if (supported_n(N)) { if (sizes && k < cap) sizes[k] = N; ++k; }
+    return k;
+}
+
+int gss_frame_count(int64_t n, int N, int H, int64_t* T, int64_t* nadd) { return frame_count(n, N, H, T, nadd); }
+
+int gss_stft_packed(const float* wave, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps, float* feat, void* stream) {
+    return stft_dispatch<float>(wave, B, n, ld, N, H, flags, eps, feat, stream);
+}
+int gss_stft_packed_i16(const int16_t* wave, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps, float* feat, void* stream) {
+    return stft_dispatch<int16_t>(wave, B, n, ld, N, H, flags, eps, feat, stream);
+}
+
+int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H, int flags, float eps, float* wave_out, int64_t ld_out, void* stream) {
+    int hs = 0;
+    if (int rc = check_nh(N, H, &hs)) return rc;
+    if (!feat || !wave_out) return fail(GSS_EINVAL, "istft: null pointer");
+    if (R < 0 || T < 2 || ld_out < (T - 1) * H) return fail(GSS_EINVAL, "istft: bad shape R=%lld T=%lld ld_out=%lld", (long long)R, (long long)T, (long long)ld_out);
+    if (flags & ~GSS_FLAG_EXP) return fail(GSS_EINVAL, "istft: unknown flags 0x%x", flags);
+    if (R == 0) return GSS_OK;
+    gss::IstftArgs a{};
+    a.feat = feat; a.out = wave_out; a.rows = R; a.T = T; a.ld_out = ld_out; a.eps = eps;
+    a.npairs = (int)((T + 1) / 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool ex = flags & GSS_FLAG_EXP;
+#define GSS_CASE(NN, HH) if (N == NN && hs == HH) return ex ? launch_istft<NN, HH, true>(a, st) : launch_istft<NN, HH, false>(a, st);
+    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
+#undef GSS_CASE
+    return fail(GSS_EUNSUPPORTED, "istft: no kernel for N=%d H=%d", N, H);
+}
+
+int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64_t n, int64_t ld, int N, int H,
+                   float* out, int64_t ld_out, void* stream) {
+    int hs = 0;
+    if (int rc = check_nh(N, H, &hs)) return rc;
+    if (!wave || !mask || !out) return fail(GSS_EINVAL, "mask_istft: null pointer");
+    if (B < 0 || S < 1 || n < 1 || ld < n) return fail(GSS_EINVAL, "mask_istft: bad shape B=%lld S=%d n=%lld ld=%lld", (long long)B, S, (long long)n, (long long)ld);
+    if (n < N) return fail(GSS_EUNSUPPORTED, "mask_istft: n=%lld < FFT_SIZE=%d", (long long)n, N);
+    gss::SynthArgs a{};
+    a.wave = wave; a.mask = mask; a.out = out; a.B = B; a.n = n; a.ld = ld; a.ld_out = ld_out; a.S = S;
+    if (int rc = frame_count(n, N, H, &a.T, nullptr)) return rc;
+    if (ld_out < (a.T - 1) * H) return fail(GSS_EINVAL, "mask_istft: ld_out=%lld < (T-1)*H=%lld", (long long)ld_out, (long long)((a.T - 1) * H));
+    if (B == 0) return GSS_OK;
+    a.npairs = (int)((a.T + 1) / 2);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GSS_CASE(NN, HH) if (N == NN && hs == HH) return synth_by_s<NN, HH>(a, st);
+    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
+#undef GSS_CASE
+    return fail(GSS_EUNSUPPORTED, "mask_istft: no kernel for N=%d H=%d", N, H);
+}
+
+int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_t T, int N, float* out, void* stream) {
+    if (!mix || !mask || !out) return fail(GSS_EINVAL, "apply_mask: null pointer");
+    if (N < 8 || N % 8) return fail(GSS_EINVAL, "apply_mask: N=%d must be a multiple of 8", N);
+    if (B < 0 || S < 1 || T < 0) return fail(GSS_EINVAL, "apply_mask: bad shape");
+    if (((uintptr_t)mix | (uintptr_t)mask | (uintptr_t)out) & 15) return fail(GSS_EINVAL, "apply_mask: buffers must be 16-byte aligned");
+    int64_t total = B * S * T * (N / 8);
+    if (total == 0) return GSS_OK;
+    gss::apply_mask_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mix, mask, out, B, S, T, N);
+    return after_launch("apply_mask_kernel");
+}
+
+static int logexp(bool ex, const float* in, float* out, int64_t rows, int N, float eps, void* stream) {
+    if (!in || !out) return fail(GSS_EINVAL, "to_log/to_exp: null pointer");
+    if (N < 8 || N % 8) return fail(GSS_EINVAL, "to_log/to_exp: N=%d must be a multiple of 8", N);
+    if (rows < 0) return fail(GSS_EINVAL, "to_log/to_exp: rows < 0");
+    if (((uintptr_t)in | (uintptr_t)out) & 15) return fail(GSS_EINVAL, "to_log/to_exp: buffers must be 16-byte aligned");
+    int64_t total = rows * (N / 8);
+    if (total == 0) return GSS_OK;
+    if (ex) gss::logexp_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, N, eps);
+    else gss::logexp_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, N, eps);
+    return after_launch("logexp_kernel");
+}
+int gss_to_log(const float* in, float* out, int64_t rows, int N, float eps, void* stream) { return logexp(false, in, out, rows, N, eps, stream); }
+int gss_to_exp(const float* in, float* out, int64_t rows, int N, float eps, void* stream) { return logexp(true, in, out, rows, N, eps, stream); }
+
+int gss_cross_snr(const float* clear, const float* noisy, int64_t B, int m, int n, int64_t L, float eps, float* snr, void* stream) {
+    if (!clear || !noisy || !snr) return fail(GSS_EINVAL, "cross_snr: null pointer");
+    if (B < 0 || m < 1 || n < 1 || L < 1) return fail(GSS_EINVAL, "cross_snr: bad shape");
+    if (B == 0) return GSS_OK;
+    gss::cross_snr_kernel<<<(unsigned)(B * m * n), 256, 0, (cudaStream_t)stream>>>(clear, noisy, m, n, L, eps, snr);
+    return after_launch("cross_snr_kernel");
+}
+
+int gss_ae_partial(const float* sep, const float* mix, int64_t B, int S, int64_t L, float* partial, void* stream) {
+    if (!sep || !mix || !partial) return fail(GSS_EINVAL, "ae_partial: null pointer");
+    if (B < 0 || S < 1 || L < 1) return fail(GSS_EINVAL, "ae_partial: bad shape");
+    if (B == 0) return GSS_OK;
+    gss::ae_partial_kernel<<<(unsigned)B, 512, 0, (cudaStream_t)stream>>>(sep, mix, S, L, partial);
+    return after_launch("ae_partial_kernel");
+}
+
+int gss_wav16_normalise(const float* x, int64_t R, int64_t len, int64_t ld, float* minmax, int16_t* pcm, void* stream) {
+    if (!x || !minmax || !pcm) return fail(GSS_EINVAL, "wav16: null pointer");
+    if (R < 0 || len < 1 || ld < len) return fail(GSS_EINVAL, "wav16: bad shape");
+    if (R == 0) return GSS_OK;
+    gss::minmax_kernel<<<(unsigned)R, 512, 0, (cudaStream_t)stream>>>(x, len, ld, minmax);
+    if (int rc = after_launch("minmax_kernel")) return rc;
+    gss::wav16_kernel<<<grid_for(R * len, 256), 256, 0, (cudaStream_t)stream>>>(x, R, len, ld, minmax, pcm);
+    return after_launch("wav16_kernel");
+}
+
+// ---- host-buffer entry points ------------------------------------------------
+int gss_stft_packed_host(const float* wave_h, int64_t B, int64_t n, int N, int H, int flags, float eps, float* feat_h) {
+    int64_t T = 0;
+    if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
+    if (!wave_h || !feat_h) return fail(GSS_EINVAL, "stft_host: null pointer");
+    if (B <= 0) return B == 0 ? GSS_OK : fail(GSS_EINVAL, "stft_host: B < 0");
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    const size_t bi = sizeof(float) * B * n, bo = sizeof(float) * B * T * N;
+    if (int rc = g_ws_in.reserve(bi)) return rc;
+    if (int rc = g_ws_out.reserve(bo)) return rc;
+    CK(cudaMemcpyAsync(g_ws_in.p, wave_h, bi, cudaMemcpyHostToDevice, 0));
+    if (int rc = gss_stft_packed((const float*)g_ws_in.p, B, n, n, N, H, flags, eps, (float*)g_ws_out.p, nullptr)) return rc;
+    CK(cudaMemcpyAsync(feat_h, g_ws_out.p, bo, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return GSS_OK;
+}
+
+int gss_istft_packed_host(const float* feat_h, int64_t R, int64_t T, int N, int H, int flags, float eps, float* wave_h) {
+    if (!feat_h || !wave_h) return fail(GSS_EINVAL, "istft_host: null pointer");
+    if (R <= 0) return R == 0 ? GSS_OK : fail(GSS_EINVAL, "istft_host: R < 0");
+    if (T < 2 || H < 1) return fail(GSS_EINVAL, "istft_host: bad shape");
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    const int64_t len = (T - 1) * H;
+    const size_t bi = sizeof(float) * R * T * N, bo = sizeof(float) * R * len;
+    if (int rc = g_ws_in.reserve(bi)) return rc;
+    if (int rc = g_ws_out.reserve(bo)) return rc;
+    CK(cudaMemcpyAsync(g_ws_in.p, feat_h, bi, cudaMemcpyHostToDevice, 0));
+    if (int rc = gss_istft_packed((const float*)g_ws_in.p, R, T, N, H, flags, eps, (float*)g_ws_out.p, len, nullptr)) return rc;
+    CK(cudaMemcpyAsync(wave_h, g_ws_out.p, bo, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return GSS_OK;
+}
+
+// Chunked pipelines: chunk k's copy overlaps chunk k-1's kernel.
+int gss_stft_h2d(const float* wave_h, float* wave_d, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps,
+                 float* feat_d, int chunks, void* stream) {
+    int64_t T = 0;
+    if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
+    if (!wave_h || !wave_d || !feat_d) return fail(GSS_EINVAL, "stft_h2d: null pointer");
+    if (chunks < 1 || ld < n) return fail(GSS_EINVAL, "stft_h2d: bad chunks/ld");
+    if (int rc = g_cs.init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t per = (B + chunks - 1) / chunks;
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
+        const int64_t nb = (B - b0 < per) ? B - b0 : per;
+        CK(cudaMemcpy2DAsync(wave_d + b0 * ld, sizeof(float) * ld, wave_h + b0 * n, sizeof(float) * n, sizeof(float) * n, nb,
+                             cudaMemcpyHostToDevice, g_cs.h2d));
+        cudaEvent_t ev = g_cs.ev[k % 8];
+        CK(cudaEventRecord(ev, g_cs.h2d));
+        CK(cudaStreamWaitEvent(st, ev, 0));
+        if (int rc = gss_stft_packed(wave_d + b0 * ld, nb, n, ld, N, H, flags, eps, feat_d + b0 * T * N, stream)) return rc;
+    }
+    CK(cudaStreamSynchronize(st));
+    return GSS_OK;
+}
+
+int gss_mask_istft_d2h(const float* wave_d, const float* mask_d, int64_t B, int S, int64_t n, int64_t ld, int N, int H,
+                       float* out_d, float* out_h, int64_t ld_out, int chunks, void* stream) {
+    int64_t T = 0;
+    if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
+    if (!out_h || !out_d) return fail(GSS_EINVAL, "mask_istft_d2h: null pointer");
+    if (chunks < 1) return fail(GSS_EINVAL, "mask_istft_d2h: bad chunks");
+    if (int rc = g_cs.init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t len = (T - 1) * H;
+    const int64_t per = (B + chunks - 1) / chunks;
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
+        const int64_t nb = (B - b0 < per) ? B - b0 : per;
+        if (int rc = gss_mask_istft(wave_d + b0 * ld, mask_d + b0 * S * T * (N / 2), nb, S, n, ld, N, H,
+                                    out_d + b0 * S * ld_out, ld_out, stream)) return rc;
+        cudaEvent_t ev = g_cs.ev[k % 8];
+        CK(cudaEventRecord(ev, st));
+        CK(cudaStreamWaitEvent(g_cs.d2h, ev, 0));
+        CK(cudaMemcpy2DAsync(out_h + b0 * S * len, sizeof(float) * len, out_d + b0 * S * ld_out, sizeof(float) * ld_out,
+                             sizeof(float) * len, nb * S, cudaMemcpyDeviceToHost, g_cs.d2h));
+    }
+    CK(cudaStreamSynchronize(g_cs.d2h));
+    return GSS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// gss_elem.cuh - the element-wise and reduction ops that sit beside the transforms:
+// to_log_signal / to_exp_signal (app/ops.py:228-251), the mask multiply,
+// batch_cross_snr (app/ops.py:191-225), the auto-encoder partial (main.py:353-361)
+// and the int16 WAV normalisation (main.py:112-116).  All HBM-bound streaming kernels:
+// 128-bit accesses, grid-stride loops sized to the SM count by the host.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "gss_stream.cuh"
+
+namespace gss {
+
+// rows x N packed features; a thread handles bins k..k+3 of both halves of a row
+template <bool EXP>
+__global__ void __launch_bounds__(256) logexp_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                     int64_t rows, int N, float eps) {
+    const int q = N / 8;                              // float4 per half row
+    const int64_t total = rows * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / q; const int k4 = (int)(i - r * q);
+        const float4* pr = reinterpret_cast<const float4*>(in + r * N) + k4;
+        float4 re = __ldg(pr), im = __ldg(pr + q);
+        float g;
+#define GSS_G(c) g = EXP ? exp_gain(re.c, im.c, eps) : log_gain(re.c, im.c, eps); re.c *= g; im.c *= g;
+        GSS_G(x) GSS_G(y) GSS_G(z) GSS_G(w)
+#undef GSS_G
+        float4* po = reinterpret_cast<float4*>(out + r * N) + k4;
+        po[0] = re; po[q] = im;
+    }
+}
+
+// mix [B,T,N], mask [B,S,T,N/2] -> out [B*S,T,N]
+__global__ void __launch_bounds__(256) apply_mask_kernel(const float* __restrict__ mix, const float* __restrict__ mask,
+                                                         float* __restrict__ out, int64_t B, int S, int64_t T, int N) {
+    const int q = N / 8;
+    const int64_t total = B * S * T * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rowo = i / q; const int k4 = (int)(i - rowo * q);   // rowo = (b*S + s)*T + t
+        const int64_t bs = rowo / T, t = rowo - bs * T, b = bs / S;
+        const float4* pm = reinterpret_cast<const float4*>(mix + (b * T + t) * N) + k4;
+        float4 g = __ldg(reinterpret_cast<const float4*>(mask + rowo * (N / 2)) + k4);
+        float4 re = __ldg(pm), im = __ldg(pm + q);
+        re.x *= g.x; re.y *= g.y; re.z *= g.z; re.w *= g.w;
+        im.x *= g.x; im.y *= g.y; im.z *= g.z; im.w *= g.w;
+        float4* po = reinterpret_cast<float4*>(out + rowo * N) + k4;
+        po[0] = re; po[q] = im;
+    }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    v = l < nw ? red[l] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one CTA per (b, i, k): snr[b,i,k] = c*(ln(mean clear_i^2 + eps) - ln(mean (clear_i - noisy_k)^2 + eps))
+__global__ void __launch_bounds__(256) cross_snr_kernel(const float* __restrict__ clear, const float* __restrict__ noisy,
+                                                        int m, int n, int64_t L, float eps, float* __restrict__ snr) {
+    __shared__ float red[32];
+    const int64_t id = blockIdx.x;
+    const int64_t b = id / (m * n); const int r = (int)(id - b * m * n); const int i = r / n, k = r - i * n;
+    const float* pc = clear + (b * m + i) * L;
+    const float* pn = noisy + (b * n + k) * L;
+    float sp = 0.f, np = 0.f;
+    const bool v4 = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(pc) | reinterpret_cast<uintptr_t>(pn)) & 15) == 0;
+    if (v4) {
+        for (int64_t x = threadIdx.x; x < L / 4; x += blockDim.x) {
+            float4 c4 = __ldg(reinterpret_cast<const float4*>(pc) + x), n4 = __ldg(reinterpret_cast<const float4*>(pn) + x);
+            float d;
+            sp = fmaf(c4.x, c4.x, sp); d = c4.x - n4.x; np = fmaf(d, d, np);
+            sp = fmaf(c4.y, c4.y, sp); d = c4.y - n4.y; np = fmaf(d, d, np);
+            sp = fmaf(c4.z, c4.z, sp); d = c4.z - n4.z; np = fmaf(d, d, np);
+            sp = fmaf(c4.w, c4.w, sp); d = c4.w - n4.w; np = fmaf(d, d, np);
+        }
+    } else {
+        for (int64_t x = threadIdx.x; x < L; x += blockDim.x) {
+            float c = __ldg(pc + x), d = c - __ldg(pn + x);
+            sp = fmaf(c, c, sp); np = fmaf(d, d, np);
+        }
+    }
+    sp = block_sum(sp, red);
+    np = block_sum(np, red);
+    if (threadIdx.x == 0)
+        snr[id] = 4.342944819f * (logf(sp / (float)L + eps) - logf(np / (float)L + eps));   // app/ops.py:188
+}
+
+// one CTA per mixture: partial[b] = sum_l (sum_s sep[b,s,l] - mix[b,l])^2
+__global__ void __launch_bounds__(512) ae_partial_kernel(const float* __restrict__ sep, const float* __restrict__ mix,
+                                                         int S, int64_t L, float* __restrict__ partial) {
+    __shared__ float red[32];
+    const int64_t b = blockIdx.x;
+    float acc = 0.f;
+    for (int64_t x = threadIdx.x; x < L; x += blockDim.x) {
+        float s = -__ldg(mix + b * L + x);
+        for (int k = 0; k < S; ++k) s += __ldg(sep + (b * S + k) * L + x);
+        acc = fmaf(s, s, acc);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[b] = acc;
+}
+
+// per-row min / max -> minmax[2r], minmax[2r+1]
+__global__ void __launch_bounds__(512) minmax_kernel(const float* __restrict__ x, int64_t len, int64_t ld, float* __restrict__ minmax) {
+    __shared__ float rlo[16], rhi[16];
+    const float* row = x + (int64_t)blockIdx.x * ld;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) { float v = __ldg(row + i); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { rlo[threadIdx.x >> 5] = lo; rhi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        lo = threadIdx.x < (blockDim.x >> 5) ? rlo[threadIdx.x] : INFINITY;
+        hi = threadIdx.x < (blockDim.x >> 5) ? rhi[threadIdx.x] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if (threadIdx.x == 0) { minmax[2 * blockIdx.x] = lo; minmax[2 * blockIdx.x + 1] = hi; }
+    }
+}
+
+// main.py:113-115: d -= min; d *= 32767/(max-min); astype(int16) (truncation), float32 arithmetic
+__global__ void __launch_bounds__(256) wav16_kernel(const float* __restrict__ x, int64_t R, int64_t len, int64_t ld,
+                                                    const float* __restrict__ minmax, int16_t* __restrict__ pcm) {
+    const int64_t total = R * len;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / len, c = i - r * len;
+        const float lo = __ldg(minmax + 2 * r), hi = __ldg(minmax + 2 * r + 1);
+        const float scale = __fdiv_rn(32767.0f, __fsub_rn(hi, lo));
+        const float d = __fmul_rn(__fsub_rn(__ldg(x + r * ld + c), lo), scale);
+        pcm[i] = (int16_t)__float2int_rz(d);
+    }
+}
+
+}  // namespace gss

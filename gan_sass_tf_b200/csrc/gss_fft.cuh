@@ -1,0 +1,294 @@
+// gss_fft.cuh - per-team complex FFT used by every spectral kernel of libgss.
+//
+// Geometry (modelled one-to-one, including the shared-memory layouts, in
+// tools/fft_model.py and checked on the host by tests/test_fft_model.py):
+//
+//   N = 64*M complex points, M in {4, 8, 16};  a "team" of TPF = N/16 threads owns
+//   one transform, 16 complex points per thread, three passes radix 8 / M / 8.
+//   L = N/8.  All arithmetic is packed FP32x2 (FADD2/FMUL2/FFMA2): a v2 holds the
+//   same quantity for the two butterflies a thread owns in a pass.
+//
+//   pass 0 : thread j, lanes e=0,1 own butterflies n' = 2j+e over x[n' + L*n0]
+//   middle : DFT-M over n1 for (k0, n2), n' = 8*n1 + n2
+//   last   : lanes (A,B) own butterflies c = {j, L-j} (thread 0: {0, L/2}) and
+//            produce Z[c + L*k2]: Z[k] and Z[N-k] end up in the same thread, so
+//            the two-for-one real split / Hermitian pack need no data exchange.
+//
+// Two real sequences ride one complex transform (re = sequence a, im = sequence b).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gss {
+
+typedef float2 v2;
+struct cv2 { v2 re, im; };
+
+__device__ __forceinline__ v2 vadd(v2 a, v2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ v2 vneg(v2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ v2 vsub(v2 a, v2 b) { return __fadd2_rn(a, vneg(b)); }
+__device__ __forceinline__ v2 vmul(v2 a, v2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ v2 vfma(v2 a, v2 b, v2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ v2 vset(float s) { return make_float2(s, s); }
+__device__ __forceinline__ v2 vswap(v2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ cv2 cadd(cv2 a, cv2 b) { cv2 r; r.re = vadd(a.re, b.re); r.im = vadd(a.im, b.im); return r; }
+__device__ __forceinline__ cv2 csub(cv2 a, cv2 b) { cv2 r; r.re = vsub(a.re, b.re); r.im = vsub(a.im, b.im); return r; }
+
+// a * w (forward) or a * conj(w) (inverse)
+template <bool INV>
+__device__ __forceinline__ cv2 cmul(cv2 a, cv2 w) {
+    cv2 r;
+    if (!INV) {
+        r.re = vfma(a.re, w.re, vneg(vmul(a.im, w.im)));
+        r.im = vfma(a.re, w.im, vmul(a.im, w.re));
+    } else {
+        r.re = vfma(a.re, w.re, vmul(a.im, w.im));
+        r.im = vfma(a.im, w.re, vneg(vmul(a.re, w.im)));
+    }
+    return r;
+}
+
+#define GSS_SQRT1_2 0.70710678118654752440f
+
+// in-place 8-point DFT, natural order in and out.  INV=false: e^{-2 pi i nk/8}.
+template <bool INV>
+__device__ __forceinline__ void dft8(cv2 (&a)[8]) {
+    cv2 b0 = cadd(a[0], a[4]), b4 = csub(a[0], a[4]);
+    cv2 b1 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]);
+    cv2 b2 = cadd(a[2], a[6]), b6 = csub(a[2], a[6]);
+    cv2 b3 = cadd(a[3], a[7]), b7 = csub(a[3], a[7]);
+    // even outputs: DFT4(b0..b3)
+    cv2 d0 = cadd(b0, b2), d1 = csub(b0, b2), d2 = cadd(b1, b3), d3 = csub(b1, b3);
+    a[0] = cadd(d0, d2);
+    a[4] = csub(d0, d2);
+    if (!INV) {   // d3 * (-i) = (d3.im, -d3.re)
+        a[2].re = vadd(d1.re, d3.im); a[2].im = vsub(d1.im, d3.re);
+        a[6].re = vsub(d1.re, d3.im); a[6].im = vadd(d1.im, d3.re);
+    } else {      // d3 * (+i) = (-d3.im, d3.re)
+        a[2].re = vsub(d1.re, d3.im); a[2].im = vadd(d1.im, d3.re);
+        a[6].re = vadd(d1.re, d3.im); a[6].im = vsub(d1.im, d3.re);
+    }
+    // odd outputs: DFT4(b4, b5*W, b6*W^2, b7*W^3), W = e^{-+ i pi/4}
+    cv2 e0, e1, t5, t7;
+    if (!INV) {
+        e0.re = vadd(b4.re, b6.im); e0.im = vsub(b4.im, b6.re);     // b4 + b6*(-i)
+        e1.re = vsub(b4.re, b6.im); e1.im = vadd(b4.im, b6.re);
+        t5.re = vadd(b5.re, b5.im); t5.im = vsub(b5.im, b5.re);     // b5*(1-i)
+        t7.re = vsub(b7.im, b7.re); t7.im = vneg(vadd(b7.im, b7.re)); // b7*(-1-i)
+    } else {
+        e0.re = vsub(b4.re, b6.im); e0.im = vadd(b4.im, b6.re);     // b4 + b6*(+i)
+        e1.re = vadd(b4.re, b6.im); e1.im = vsub(b4.im, b6.re);
+        t5.re = vsub(b5.re, b5.im); t5.im = vadd(b5.im, b5.re);     // b5*(1+i)
+        t7.re = vneg(vadd(b7.re, b7.im)); t7.im = vsub(b7.re, b7.im); // b7*(-1+i)
+    }
+    cv2 u = cadd(t5, t7), v = csub(t5, t7);      // both still to be scaled by 1/sqrt2
+    const v2 s = vset(GSS_SQRT1_2), ms = vset(-GSS_SQRT1_2);
+    a[1].re = vfma(u.re, s, e0.re);  a[1].im = vfma(u.im, s, e0.im);
+    a[5].re = vfma(u.re, ms, e0.re); a[5].im = vfma(u.im, ms, e0.im);
+    if (!INV) {   // e3 = s*v*(-i) = s*(v.im, -v.re)
+        a[3].re = vfma(v.im, s, e1.re);  a[3].im = vfma(v.re, ms, e1.im);
+        a[7].re = vfma(v.im, ms, e1.re); a[7].im = vfma(v.re, s, e1.im);
+    } else {      // e3 = s*v*(+i) = s*(-v.im, v.re)
+        a[3].re = vfma(v.im, ms, e1.re); a[3].im = vfma(v.re, s, e1.im);
+        a[7].re = vfma(v.im, s, e1.re);  a[7].im = vfma(v.re, ms, e1.im);
+    }
+}
+
+// in-place 4-point DFT
+template <bool INV>
+__device__ __forceinline__ void dft4(cv2 (&a)[4]) {
+    cv2 d0 = cadd(a[0], a[2]), d1 = csub(a[0], a[2]), d2 = cadd(a[1], a[3]), d3 = csub(a[1], a[3]);
+    a[0] = cadd(d0, d2);
+    a[2] = csub(d0, d2);
+    if (!INV) {
+        a[1].re = vadd(d1.re, d3.im); a[1].im = vsub(d1.im, d3.re);
+        a[3].re = vsub(d1.re, d3.im); a[3].im = vadd(d1.im, d3.re);
+    } else {
+        a[1].re = vsub(d1.re, d3.im); a[1].im = vadd(d1.im, d3.re);
+        a[3].re = vadd(d1.re, d3.im); a[3].im = vsub(d1.im, d3.re);
+    }
+}
+
+// ---------------------------------------------------------------------------
+template <int N_>
+struct Geo {
+    static constexpr int N = N_;
+    static constexpr int M = N / 64;          // middle radix
+    static constexpr int TPF = N / 16;        // threads per transform
+    static constexpr int L = N / 8;
+    static constexpr int P0 = TPF + 4;        // E0 pitch, float4 units
+    static constexpr int P1 = L + 4;          // E1 pitch, floats
+    static constexpr int E0_F4 = 8 * P0;      // float4 count
+    static constexpr int E1_PLANE = 8 * P1;   // floats per plane
+    static constexpr int TEAM_FLOATS = E0_F4 * 4 + 2 * E1_PLANE;
+    static constexpr int TW1_F4 = 4 * (M + 1);   // middle twiddles, [q][k1] padded, float4 (re0,re1,im0,im1)
+    static_assert(M == 8, "this round implements N = 512 (M = 8); 256/1024 are wired in fft_model.py only");
+};
+
+// per-thread constants of a team member
+template <int N>
+struct TeamCtx {
+    int j;            // thread index inside the team
+    int cA, cB;       // last-pass butterflies
+    float4* e0;       // team exchange buffer 0
+    float* e1;        // team exchange buffer 1 (re plane, im plane at +E1_PLANE)
+    const float4* tw1;  // CTA-shared middle twiddle table
+    cv2 tw0[8];       // pass-0 twiddles W_N^{(2j+e)*k0}, k0 = 1..7 ([0] unused)
+};
+
+__device__ __forceinline__ void team_sync() { __syncwarp(); }
+
+// fill the CTA-shared middle-twiddle table: entry [q*(M+1) + k1] = W_L^{(2q+e)*k1}
+template <int N>
+__device__ __forceinline__ void fill_tw1(float4* tw1, int tid, int nthreads) {
+    typedef Geo<N> G;
+    for (int i = tid; i < 4 * G::M; i += nthreads) {
+        int q = i / G::M, k1 = i % G::M;
+        float s0, c0, s1, c1;
+        sincospif(-2.0f * (float)((2 * q) * k1) / (float)G::L, &s0, &c0);
+        sincospif(-2.0f * (float)((2 * q + 1) * k1) / (float)G::L, &s1, &c1);
+        tw1[q * (G::M + 1) + k1] = make_float4(c0, c1, s0, s1);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void team_init(TeamCtx<N>& c, int j, float* team_smem, const float4* tw1) {
+    typedef Geo<N> G;
+    c.j = j;
+    c.cA = j ? j : 0;
+    c.cB = j ? G::L - j : G::L / 2;
+    c.e0 = reinterpret_cast<float4*>(team_smem);
+    c.e1 = team_smem + G::E0_F4 * 4;
+    c.tw1 = tw1;
+#pragma unroll
+    for (int k0 = 1; k0 < 8; ++k0) {
+        float s0, c0, s1, c1;
+        sincospif(-2.0f * (float)((2 * j) * k0) / (float)N, &s0, &c0);
+        sincospif(-2.0f * (float)((2 * j + 1) * k0) / (float)N, &s1, &c1);
+        c.tw0[k0].re = make_float2(c0, c1);
+        c.tw0[k0].im = make_float2(s0, s1);
+    }
+}
+
+// thread-0 re-pairing so that (Z[i].x, Z[7-i].y) and (Z[i].y, Z[7-i].x) are always
+// (Z[k], Z[N-k]) pairs; see fft_model.fixup_thread0 / unfix_thread0.
+__device__ __forceinline__ void fixup_thread0(cv2 (&z)[8], bool t0) {
+    v2 r4 = z[4].re, r5 = z[5].re, r6 = z[6].re, r7 = z[7].re;
+    v2 i4 = z[4].im, i5 = z[5].im, i6 = z[6].im, i7 = z[7].im;
+    if (t0) {
+        z[4].re = make_float2(r4.y, r5.x); z[4].im = make_float2(i4.y, i5.x);
+        z[5].re = make_float2(r5.y, r6.x); z[5].im = make_float2(i5.y, i6.x);
+        z[6].re = make_float2(r6.y, r7.x); z[6].im = make_float2(i6.y, i7.x);
+        z[7].re = make_float2(r7.y, r4.x); z[7].im = make_float2(i7.y, i4.x);
+    }
+}
+__device__ __forceinline__ void unfix_thread0(cv2 (&z)[8], bool t0) {
+    v2 r4 = z[4].re, r5 = z[5].re, r6 = z[6].re, r7 = z[7].re;
+    v2 i4 = z[4].im, i5 = z[5].im, i6 = z[6].im, i7 = z[7].im;
+    if (t0) {   // A[4..7] = [B''7, B''4, B''5, B''6];  B[4..7] = A''[4..7]
+        z[4].re = make_float2(r7.y, r4.x); z[4].im = make_float2(i7.y, i4.x);
+        z[5].re = make_float2(r4.y, r5.x); z[5].im = make_float2(i4.y, i5.x);
+        z[6].re = make_float2(r5.y, r6.x); z[6].im = make_float2(i5.y, i6.x);
+        z[7].re = make_float2(r6.y, r7.x); z[7].im = make_float2(i6.y, i7.x);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// forward: a[n0] (lanes e=0,1: samples 2j+e + L*n0; re = sequence a, im = sequence b)
+//       -> a[k2] (lanes A,B: Z[cA + L*k2], Z[cB + L*k2]) after the thread-0 fix-up.
+template <int N>
+__device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
+    typedef Geo<N> G;
+    const int j = c.j;
+    team_sync();   // the previous transform's last read of the exchange buffers
+    dft8<false>(a);
+    c.e0[j] = make_float4(a[0].re.x, a[0].re.y, a[0].im.x, a[0].im.y);
+#pragma unroll
+    for (int k0 = 1; k0 < 8; ++k0) {
+        cv2 t = cmul<false>(a[k0], c.tw0[k0]);
+        c.e0[k0 * G::P0 + j] = make_float4(t.re.x, t.re.y, t.im.x, t.im.y);
+    }
+    team_sync();
+    {   // middle (M = 8): thread (k0 = j/4, q = j%4), lanes n2 = 2q+e
+        const int k0 = j >> 2, q = j & 3;
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            float4 v = c.e0[k0 * G::P0 + 4 * n1 + q];
+            a[n1].re = make_float2(v.x, v.y);
+            a[n1].im = make_float2(v.z, v.w);
+        }
+        dft8<false>(a);
+        float* re0 = c.e1 + (2 * q) * G::P1 + k0;
+        float* re1 = re0 + G::P1;
+        re0[0] = a[0].re.x; re1[0] = a[0].re.y;
+        re0[G::E1_PLANE] = a[0].im.x; re1[G::E1_PLANE] = a[0].im.y;
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) {
+            float4 w = c.tw1[q * (G::M + 1) + k1];
+            cv2 tw; tw.re = make_float2(w.x, w.y); tw.im = make_float2(w.z, w.w);
+            cv2 t = cmul<false>(a[k1], tw);
+            re0[8 * k1] = t.re.x; re1[8 * k1] = t.re.y;
+            re0[8 * k1 + G::E1_PLANE] = t.im.x; re1[8 * k1 + G::E1_PLANE] = t.im.y;
+        }
+    }
+    team_sync();
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) {
+        const float* p = c.e1 + n2 * G::P1;
+        a[n2].re = make_float2(p[c.cA], p[c.cB]);
+        a[n2].im = make_float2(p[c.cA + G::E1_PLANE], p[c.cB + G::E1_PLANE]);
+    }
+    dft8<false>(a);
+    fixup_thread0(a, j == 0);
+}
+
+// inverse (unnormalised, e^{+...}): a[k2] in the fixed-up last-pass layout
+//       -> a[n0] (lanes e=0,1: samples 2j+e + L*n0; re/im = the two real sequences).
+template <int N>
+__device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8]) {
+    typedef Geo<N> G;
+    const int j = c.j;
+    unfix_thread0(a, j == 0);
+    team_sync();   // the previous transform's last read of the exchange buffers
+    dft8<true>(a);
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) {
+        float* p = c.e1 + n2 * G::P1;
+        p[c.cA] = a[n2].re.x; p[c.cB] = a[n2].re.y;
+        p[c.cA + G::E1_PLANE] = a[n2].im.x; p[c.cB + G::E1_PLANE] = a[n2].im.y;
+    }
+    team_sync();
+    {
+        const int k0 = j >> 2, q = j & 3;
+        const float* re0 = c.e1 + (2 * q) * G::P1 + k0;
+        const float* re1 = re0 + G::P1;
+        a[0].re = make_float2(re0[0], re1[0]);
+        a[0].im = make_float2(re0[G::E1_PLANE], re1[G::E1_PLANE]);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) {
+            cv2 t;
+            t.re = make_float2(re0[8 * k1], re1[8 * k1]);
+            t.im = make_float2(re0[8 * k1 + G::E1_PLANE], re1[8 * k1 + G::E1_PLANE]);
+            float4 w = c.tw1[q * (G::M + 1) + k1];
+            cv2 tw; tw.re = make_float2(w.x, w.y); tw.im = make_float2(w.z, w.w);
+            a[k1] = cmul<true>(t, tw);
+        }
+        dft8<true>(a);
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1)
+            c.e0[k0 * G::P0 + 4 * n1 + q] = make_float4(a[n1].re.x, a[n1].re.y, a[n1].im.x, a[n1].im.y);
+    }
+    team_sync();
+    {
+        float4 v = c.e0[j];
+        a[0].re = make_float2(v.x, v.y); a[0].im = make_float2(v.z, v.w);
+#pragma unroll
+        for (int k0 = 1; k0 < 8; ++k0) {
+            v = c.e0[k0 * G::P0 + j];
+            cv2 t; t.re = make_float2(v.x, v.y); t.im = make_float2(v.z, v.w);
+            a[k0] = cmul<true>(t, c.tw0[k0]);
+        }
+    }
+    dft8<true>(a);
+}
+
+}  // namespace gss

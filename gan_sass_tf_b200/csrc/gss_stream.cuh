@@ -1,0 +1,473 @@
+// gss_stream.cuh - the three streaming kernels of the spectral hot path.
+//
+// One FFT "team" (Geo<N>::TPF threads, one warp at N = 512) walks a run of
+// consecutive frame PAIRS (2q, 2q+1) of one utterance.  Everything that
+// overlaps between frames lives in registers:
+//
+//   analysis  : a ring of raw sample "slots" (slot = L = N/8 samples, v2 per
+//               thread); each sample is loaded from global memory once per team
+//               although it belongs to N/H frames.
+//   synthesis : an overlap-add accumulator of 8+HS slots per output row; the
+//               2*HS oldest slots are complete after every pair and are
+//               written straight to global memory (no atomics, no shared
+//               memory round trip).
+//
+// Shared memory is used only for the two register exchanges inside each FFT
+// (gss_fft.cuh), private to the team, synchronised with __syncwarp.
+//
+// HS = H / L is the hop in slots: 1 (H = N/8), 2 (H = N/4), 4 (H = N/2, the
+// reference's SciPy default, main.py:97).  Positions are "padded" coordinates of
+// scipy.signal.stft(boundary='zeros'): padded index pp = p + N/2.
+#pragma once
+#include <stdint.h>
+#include "gss_fft.cuh"
+
+namespace gss {
+
+template <int N_, int HS_>
+struct SGeo {
+    typedef Geo<N_> G;
+    static constexpr int N = N_;
+    static constexpr int HS = HS_;
+    static constexpr int L = G::L;
+    static constexpr int H = HS * L;
+    static constexpr int R = 8 / HS;            // frames covering one sample
+    static constexpr int RS = 8 + HS;           // slots spanned by a frame pair
+    static constexpr int ADV = 2 * HS;          // slots advanced per pair
+    static constexpr int KEEP = RS - ADV;       // slots carried to the next pair
+    static constexpr int HALO = R / 2;          // pairs to recompute before an owned run (ceil((R-1)/2))
+    static constexpr bool CONST_NORM = (R >= 4); // sum_t w^2 is 3R/8 in the interior
+    static_assert(HS == 1 || HS == 2 || HS == 4, "hop must be N/8, N/4 or N/2");
+};
+
+// periodic Hann (scipy.signal.get_window('hann', N)): 0.5 - 0.5 cos(2 pi i / N)
+template <int N>
+__device__ __forceinline__ float hann(int i) { return 0.5f - 0.5f * cospif(2.0f * (float)i / (float)N); }
+
+// ---------------------------------------------------------------------------
+// sample access: the pair (p, p+1), p even, zero outside [0, n)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ v2 load_pair(const float* row, int64_t n, int64_t p, bool al) {
+    if (p >= 0 && p + 1 < n) {
+        if (al) return __ldg(reinterpret_cast<const float2*>(row + p));
+        return make_float2(__ldg(row + p), __ldg(row + p + 1));
+    }
+    v2 r = make_float2(0.f, 0.f);
+    if (p >= 0 && p < n) r.x = __ldg(row + p);
+    return r;
+}
+__device__ __forceinline__ v2 load_pair(const int16_t* row, int64_t n, int64_t p, bool al) {
+    if (p >= 0 && p + 1 < n) {
+        if (al) { short2 s = __ldg(reinterpret_cast<const short2*>(row + p)); return make_float2((float)s.x, (float)s.y); }
+        return make_float2((float)__ldg(row + p), (float)__ldg(row + p + 1));
+    }
+    v2 r = make_float2(0.f, 0.f);
+    if (p >= 0 && p < n) r.x = (float)__ldg(row + p);
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// to_log_signal / to_exp_signal gains (app/ops.py:228-251) for one complex bin
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float log_gain(float re, float im, float eps) {
+    float a2 = fmaf(re, re, im * im);
+    return 0.5f * log1pf(a2) * rsqrtf(a2 + eps);
+}
+__device__ __forceinline__ float exp_gain(float re, float im, float eps) {
+    float a = sqrtf(fmaf(re, re, fmaf(im, im, eps)));
+    return expm1f(a) / a;
+}
+
+// per-thread spectrum of a frame pair: bins k = c + L*i, lane x: c = cA, lane y: c = cB
+struct PairSpec {
+    v2 ar[4], ai[4];   // frame a: "re" slot feat[k], "im" slot feat[N/2 + k]
+    v2 br[4], bi[4];   // frame b
+};
+
+// two-for-one split of the forward transform (window carries the 1/2 and 1/sum(w)).
+template <int N>
+__device__ __forceinline__ void split_pair(const cv2 (&a)[8], bool t0, PairSpec& s) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v2 pre = a[i].re, pim = a[i].im;
+        v2 qre = vswap(a[7 - i].re), qim = vswap(a[7 - i].im);
+        s.ar[i] = vadd(pre, qre); s.ai[i] = vsub(pim, qim);
+        s.br[i] = vadd(pim, qim); s.bi[i] = vsub(qre, pre);
+        if (i == 0 && t0) {   // lane x of thread 0 holds (Z[0], Z[N/2]): DC in "re", Nyquist in "im"
+            s.ar[0].x = 2.f * pre.x; s.ai[0].x = 2.f * qre.x;
+            s.br[0].x = 2.f * pim.x; s.bi[0].x = 2.f * qim.x;
+        }
+    }
+}
+
+// Hermitian pack of two real-signal spectra into one complex transform input
+template <int N>
+__device__ __forceinline__ void pack_pair(const v2 (&yar)[4], const v2 (&yai)[4], const v2 (&ybr)[4], const v2 (&ybi)[4],
+                                          bool t0, cv2 (&a)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v2 pre = vsub(yar[i], ybi[i]), pim = vadd(yai[i], ybr[i]);
+        v2 qre = vadd(yar[i], ybi[i]), qim = vsub(ybr[i], yai[i]);
+        if (i == 0 && t0) {
+            pre.x = yar[0].x; pim.x = ybr[0].x;
+            qre.x = yai[0].x; qim.x = ybi[0].x;
+        }
+        a[i].re = pre; a[i].im = pim;
+        a[7 - i].re = vswap(qre); a[7 - i].im = vswap(qim);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// overlap-add output: one slot of v2 per thread, trimmed to [N/2, N/2 + (T-1)H)
+// ---------------------------------------------------------------------------
+template <class SG>
+struct OlaOut {
+    float* row;          // output row (sample 0 = padded position N/2)
+    int64_t T;
+    int j;
+    bool al;             // row is 8-byte aligned
+    v2 invn[SG::HS];     // 1 / sum_t w^2 per slot residue (only when !CONST_NORM)
+
+    __device__ __forceinline__ void init(float* row_, int64_t T_, int j_) {
+        row = row_; T = T_; j = j_;
+        al = (reinterpret_cast<uintptr_t>(row_) & 7) == 0;
+        if (!SG::CONST_NORM) {
+#pragma unroll
+            for (int m = 0; m < SG::HS; ++m) {
+                float s0 = 0.f, s1 = 0.f;
+                for (int r = 0; r < SG::R; ++r) {
+                    float w0 = hann<SG::N>(m * SG::L + 2 * j + r * SG::H);
+                    float w1 = hann<SG::N>(m * SG::L + 2 * j + 1 + r * SG::H);
+                    s0 += w0 * w0; s1 += w1 * w1;
+                }
+                invn[m] = make_float2(1.f / s0, 1.f / s1);
+            }
+        }
+    }
+    // actual sum_t w^2[pp - tH] over the frames that exist (edges of the signal)
+    __device__ __forceinline__ float norm_at(int64_t sl, int e) const {
+        int64_t tlo = sl - 7; tlo = tlo <= 0 ? 0 : (tlo + SG::HS - 1) / SG::HS;
+        int64_t thi = sl / SG::HS; if (thi > T - 1) thi = T - 1;
+        float s = 0.f;
+        for (int64_t t = tlo; t <= thi; ++t) {
+            int i = (int)((sl - t * SG::HS) * SG::L) + 2 * j + e;
+            float w = hann<SG::N>(i);
+            s += w * w;
+        }
+        return s > 1e-10f ? s : 1.0f;     // scipy.signal.istft: where(norm > 1e-10, norm, 1)
+    }
+    __device__ __forceinline__ void write(int64_t sl, int m /* sl mod HS, static */, v2 v) const {
+        if (sl < 4 || sl >= 4 + (T - 1) * SG::HS) return;
+        if (SG::CONST_NORM) {
+            if (sl <= 7 - SG::HS || sl >= T * SG::HS) {       // fewer than R frames cover this slot
+                const float c = 0.375f * SG::R;
+                v.x *= c / norm_at(sl, 0); v.y *= c / norm_at(sl, 1);
+            }
+        } else {
+            v = vmul(v, invn[m]);
+        }
+        float* p = row + (sl - 4) * SG::L + 2 * j;
+        if (al) *reinterpret_cast<float2*>(p) = v; else { p[0] = v.x; p[1] = v.y; }
+    }
+};
+
+// analysis / synthesis windows at this thread's sample positions
+template <class SG>
+__device__ __forceinline__ void make_window(int j, float scale, v2 (&w)[8]) {
+#pragma unroll
+    for (int n0 = 0; n0 < 8; ++n0)
+        w[n0] = make_float2(scale * hann<SG::N>(2 * j + SG::L * n0), scale * hann<SG::N>(2 * j + 1 + SG::L * n0));
+}
+
+struct ChunkPlan { int ppc; int nchunk; };   // pairs per chunk, chunks per row
+
+// ---------------------------------------------------------------------------
+// STFT: wave [B, ld] -> packed feature [B, T, N] (+ to_log)      A1 + A2 (+ A3)
+// ---------------------------------------------------------------------------
+template <typename TIn>
+struct StftArgs {
+    const TIn* wave; float* feat;
+    int64_t B, n, ld, T;
+    int npairs, ppc, nchunk;
+    float eps;
+};
+
+template <int N, int HS, bool LOG, typename TIn, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) stft_kernel(const StftArgs<TIn> p) {
+    typedef SGeo<N, HS> SG; typedef Geo<N> G;
+    extern __shared__ float4 smem4[];
+    float* smf = reinterpret_cast<float*>(smem4);
+    fill_tw1<N>(smem4, threadIdx.x, WARPS * 32);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
+    if (item >= p.B * p.nchunk) return;
+    const int64_t b = item / p.nchunk;
+    const int c = (int)(item - b * p.nchunk);
+    const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
+
+    TeamCtx<N> ctx;
+    team_init<N>(ctx, j, smf + 4 * G::TW1_F4 + warp * G::TEAM_FLOATS, smem4);
+    v2 win[8];
+    make_window<SG>(j, 1.0f / (float)N, win);      // 1/sum(w) = 2/N, and the 1/2 of the two-for-one split
+
+    const TIn* row = p.wave + b * p.ld;
+    const bool al = (reinterpret_cast<uintptr_t>(row) % (2 * sizeof(TIn))) == 0;
+    int64_t base = (int64_t)2 * q0 * HS;            // padded slot of ring[0]
+    auto ld_slot = [&](int64_t sl) { return load_pair(row, p.n, (sl - 4) * SG::L + 2 * j, al); };
+
+    v2 ring[SG::RS], nxt[SG::ADV];
+#pragma unroll
+    for (int i = 0; i < SG::KEEP; ++i) ring[i] = ld_slot(base + i);
+#pragma unroll
+    for (int i = 0; i < SG::ADV; ++i) nxt[i] = ld_slot(base + SG::KEEP + i);
+
+    for (int q = q0; q < q1; ++q) {
+#pragma unroll
+        for (int i = 0; i < SG::ADV; ++i) ring[SG::KEEP + i] = nxt[i];
+        if (q + 1 < q1) {
+#pragma unroll
+            for (int i = 0; i < SG::ADV; ++i) nxt[i] = ld_slot(base + SG::RS + i);
+        }
+        cv2 a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], win[i]); a[i].im = vmul(ring[HS + i], win[i]); }
+        fft_forward<N>(ctx, a);
+        PairSpec s;
+        split_pair<N>(a, j == 0, s);
+
+        const int64_t ta = 2 * (int64_t)q;
+        float* ra = p.feat + (b * p.T + ta) * N;
+        const bool hb = ta + 1 < p.T;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (LOG) {
+                float g;
+                g = log_gain(s.ar[i].x, s.ai[i].x, p.eps); s.ar[i].x *= g; s.ai[i].x *= g;
+                g = log_gain(s.ar[i].y, s.ai[i].y, p.eps); s.ar[i].y *= g; s.ai[i].y *= g;
+                g = log_gain(s.br[i].x, s.bi[i].x, p.eps); s.br[i].x *= g; s.bi[i].x *= g;
+                g = log_gain(s.br[i].y, s.bi[i].y, p.eps); s.br[i].y *= g; s.bi[i].y *= g;
+            }
+            const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
+            ra[kx] = s.ar[i].x; ra[N / 2 + kx] = s.ai[i].x;
+            ra[ky] = s.ar[i].y; ra[N / 2 + ky] = s.ai[i].y;
+            if (hb) {
+                ra[N + kx] = s.br[i].x; ra[N + N / 2 + kx] = s.bi[i].x;
+                ra[N + ky] = s.br[i].y; ra[N + N / 2 + ky] = s.bi[i].y;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SG::KEEP; ++i) ring[i] = ring[i + SG::ADV];
+        base += SG::ADV;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// iSTFT: packed feature [R, T, N] (+ to_exp) -> wave [R, ld_out]   (A5 +) A6 + A8
+// ---------------------------------------------------------------------------
+struct IstftArgs {
+    const float* feat; float* out;
+    int64_t rows, T, ld_out;
+    int npairs, ppc, nchunk;
+    float eps;
+};
+
+template <int N, int HS, bool EXP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
+    typedef SGeo<N, HS> SG; typedef Geo<N> G;
+    extern __shared__ float4 smem4[];
+    float* smf = reinterpret_cast<float*>(smem4);
+    fill_tw1<N>(smem4, threadIdx.x, WARPS * 32);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
+    if (item >= p.rows * p.nchunk) return;
+    const int64_t r = item / p.nchunk;
+    const int c = (int)(item - r * p.nchunk);
+    const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
+    const int qs = max(q0 - SG::HALO, 0);
+
+    TeamCtx<N> ctx;
+    team_init<N>(ctx, j, smf + 4 * G::TW1_F4 + warp * G::TEAM_FLOATS, smem4);
+    v2 win[8];
+    // frame = sum(w) * irfft = (N/2)(1/N) * raw inverse; interior 1/sum(w^2) folded in when constant
+    make_window<SG>(j, SG::CONST_NORM ? 0.5f / (0.375f * SG::R) : 0.5f, win);
+    OlaOut<SG> o;
+    o.init(p.out + r * p.ld_out, p.T, j);
+
+    v2 acc[SG::RS];
+#pragma unroll
+    for (int i = 0; i < SG::RS; ++i) acc[i] = make_float2(0.f, 0.f);
+    int64_t base = (int64_t)2 * qs * HS;
+    const float* frow = p.feat + r * p.T * N;
+
+    for (int q = qs; q < q1; ++q) {
+        const int64_t ta = 2 * (int64_t)q;
+        const float* ra = frow + ta * N;
+        const bool hb = ta + 1 < p.T;
+        v2 yar[4], yai[4], ybr[4], ybi[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
+            yar[i] = make_float2(__ldg(ra + kx), __ldg(ra + ky));
+            yai[i] = make_float2(__ldg(ra + N / 2 + kx), __ldg(ra + N / 2 + ky));
+            if (hb) {
+                ybr[i] = make_float2(__ldg(ra + N + kx), __ldg(ra + N + ky));
+                ybi[i] = make_float2(__ldg(ra + N + N / 2 + kx), __ldg(ra + N + N / 2 + ky));
+            } else {
+                ybr[i] = make_float2(0.f, 0.f); ybi[i] = make_float2(0.f, 0.f);
+            }
+            if (EXP) {
+                float g;
+                g = exp_gain(yar[i].x, yai[i].x, p.eps); yar[i].x *= g; yai[i].x *= g;
+                g = exp_gain(yar[i].y, yai[i].y, p.eps); yar[i].y *= g; yai[i].y *= g;
+                g = exp_gain(ybr[i].x, ybi[i].x, p.eps); ybr[i].x *= g; ybi[i].x *= g;
+                g = exp_gain(ybr[i].y, ybi[i].y, p.eps); ybr[i].y *= g; ybi[i].y *= g;
+            }
+        }
+        cv2 a[8];
+        pack_pair<N>(yar, yai, ybr, ybi, j == 0, a);
+        fft_inverse<N>(ctx, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i] = vfma(a[i].re, win[i], acc[i]);
+            acc[HS + i] = vfma(a[i].im, win[i], acc[HS + i]);
+        }
+        if (q >= q0) {
+#pragma unroll
+            for (int i = 0; i < SG::ADV; ++i) o.write(base + i, i % HS, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < SG::KEEP; ++i) acc[i] = acc[i + SG::ADV];
+#pragma unroll
+        for (int i = SG::KEEP; i < SG::RS; ++i) acc[i] = make_float2(0.f, 0.f);
+        base += SG::ADV;
+    }
+    if (c == p.nchunk - 1) {
+#pragma unroll
+        for (int i = 0; i < SG::KEEP; ++i) o.write(base + i, i % HS, acc[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fused synthesis: wave [B, ld], mask [B, S, T, N/2] -> out [B*S, ld_out]   A1 + A7 + A8
+// The mixture spectrum is recomputed from the waveform (4n bytes) instead of being
+// re-read (4TN bytes).  ST sources are carried per pass; S > ST runs as separate
+// items (source groups) that each recompute the forward transform.
+// ---------------------------------------------------------------------------
+struct SynthArgs {
+    const float* wave; const float* mask; float* out;
+    int64_t B, n, ld, T, ld_out;
+    int S, ngroups;                 // ngroups = ceil(S / ST)
+    int npairs, ppc, nchunk;
+};
+
+template <int N, int HS, int ST, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs p) {
+    typedef SGeo<N, HS> SG; typedef Geo<N> G;
+    extern __shared__ float4 smem4[];
+    float* smf = reinterpret_cast<float*>(smem4);
+    fill_tw1<N>(smem4, threadIdx.x, WARPS * 32);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t per_b = (int64_t)p.ngroups * p.nchunk;
+    if (item >= p.B * per_b) return;
+    const int64_t b = item / per_b;
+    const int rem = (int)(item - b * per_b);
+    const int grp = rem / p.nchunk, c = rem - grp * p.nchunk;
+    const int s0 = grp * ST;
+    const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
+    const int qs = max(q0 - SG::HALO, 0);
+
+    TeamCtx<N> ctx;
+    team_init<N>(ctx, j, smf + 4 * G::TW1_F4 + warp * G::TEAM_FLOATS, smem4);
+    v2 winf[8], wini[8];
+    make_window<SG>(j, 1.0f / (float)N, winf);
+    make_window<SG>(j, SG::CONST_NORM ? 0.5f / (0.375f * SG::R) : 0.5f, wini);
+
+    OlaOut<SG> o[ST];
+#pragma unroll
+    for (int s = 0; s < ST; ++s) o[s].init(p.out + (b * p.S + min(s0 + s, p.S - 1)) * p.ld_out, p.T, j);
+
+    const float* row = p.wave + b * p.ld;
+    const bool al = (reinterpret_cast<uintptr_t>(row) & 7) == 0;
+    auto ld_slot = [&](int64_t sl) { return load_pair(row, p.n, (sl - 4) * SG::L + 2 * j, al); };
+    const int NH = N / 2;
+
+    v2 acc[ST][SG::RS];
+#pragma unroll
+    for (int s = 0; s < ST; ++s)
+#pragma unroll
+        for (int i = 0; i < SG::RS; ++i) acc[s][i] = make_float2(0.f, 0.f);
+
+    int64_t base = (int64_t)2 * qs * HS;
+    v2 ring[SG::RS], nxt[SG::ADV];
+#pragma unroll
+    for (int i = 0; i < SG::KEEP; ++i) ring[i] = ld_slot(base + i);
+#pragma unroll
+    for (int i = 0; i < SG::ADV; ++i) nxt[i] = ld_slot(base + SG::KEEP + i);
+
+    for (int q = qs; q < q1; ++q) {
+#pragma unroll
+        for (int i = 0; i < SG::ADV; ++i) ring[SG::KEEP + i] = nxt[i];
+        if (q + 1 < q1) {
+#pragma unroll
+            for (int i = 0; i < SG::ADV; ++i) nxt[i] = ld_slot(base + SG::RS + i);
+        }
+        PairSpec x;
+        {
+            cv2 a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], winf[i]); a[i].im = vmul(ring[HS + i], winf[i]); }
+            fft_forward<N>(ctx, a);
+            split_pair<N>(a, j == 0, x);
+        }
+        const int64_t ta = 2 * (int64_t)q;
+        const bool hb = ta + 1 < p.T;
+#pragma unroll
+        for (int s = 0; s < ST; ++s) {
+            if (s0 + s < p.S) {
+                const float* ma = p.mask + (((b * p.S + s0 + s) * p.T) + ta) * NH;
+                v2 yar[4], yai[4], ybr[4], ybi[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
+                    v2 ga = make_float2(__ldg(ma + kx), __ldg(ma + ky));
+                    v2 gb = hb ? make_float2(__ldg(ma + NH + kx), __ldg(ma + NH + ky)) : make_float2(0.f, 0.f);
+                    yar[i] = vmul(x.ar[i], ga); yai[i] = vmul(x.ai[i], ga);
+                    ybr[i] = vmul(x.br[i], gb); ybi[i] = vmul(x.bi[i], gb);
+                }
+                cv2 a[8];
+                pack_pair<N>(yar, yai, ybr, ybi, j == 0, a);
+                fft_inverse<N>(ctx, a);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[s][i] = vfma(a[i].re, wini[i], acc[s][i]);
+                    acc[s][HS + i] = vfma(a[i].im, wini[i], acc[s][HS + i]);
+                }
+                if (q >= q0) {
+#pragma unroll
+                    for (int i = 0; i < SG::ADV; ++i) o[s].write(base + i, i % HS, acc[s][i]);
+                }
+#pragma unroll
+                for (int i = 0; i < SG::KEEP; ++i) acc[s][i] = acc[s][i + SG::ADV];
+#pragma unroll
+                for (int i = SG::KEEP; i < SG::RS; ++i) acc[s][i] = make_float2(0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SG::KEEP; ++i) ring[i] = ring[i + SG::ADV];
+        base += SG::ADV;
+    }
+    if (c == p.nchunk - 1) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s)
+            if (s0 + s < p.S) {
+#pragma unroll
+                for (int i = 0; i < SG::KEEP; ++i) o[s].write(base + i, i % HS, acc[s][i]);
+            }
+    }
+}
+
+}  // namespace gss

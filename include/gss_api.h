@@ -1,0 +1,131 @@
+/*
+ * gss_api.h - C ABI of libgss, the B200 (sm_100a) spectral hot path that replaces
+ * the host-side SciPy/NumPy transforms of ahmedassal/GAN_SASS_TF.
+ *
+ * Plain C: pointers, sizes, an opaque stream handle.  No torch types.  Every
+ * entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - N  = FFT_SIZE (app/hparams.py:12), power of two in [256, 1024] this round;
+ *     H  = hop, one of N/2 (the reference's SciPy default), N/4, N/8.
+ *   - "packed feature" = the reference's [T, N] float32 layout of app/utils.py:8-26:
+ *     feat[t,k]=Re X[k] (0<=k<N/2), feat[t,N/2]=Re X[N/2], feat[t,N/2+k]=Im X[k].
+ *   - Device entry points only enqueue work on `stream` (a cudaStream_t cast to
+ *     void*; NULL = legacy default stream); they never synchronise or allocate.
+ *     Host entry points (suffix _host) copy in/out themselves and return after the
+ *     result is in the host buffer.
+ *   - All functions return 0 on success or a negative gss_status; the message is
+ *     available from gss_last_error() (thread-local).
+ */
+#ifndef GSS_API_H
+#define GSS_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GSS_OK = 0,
+    GSS_EINVAL = -1,        /* bad shape / pointer / alignment                      */
+    GSS_EUNSUPPORTED = -2,  /* (N, H, S) outside the supported set, or N > n        */
+    GSS_ECUDA = -3,         /* a CUDA runtime call failed                           */
+    GSS_ENOMEM = -4         /* workspace allocation failed (host entry points only) */
+} gss_status;
+
+enum {
+    GSS_FLAG_LOG = 1,       /* fuse to_log_signal (app/ops.py:228-238) into the STFT epilogue  */
+    GSS_FLAG_EXP = 2        /* fuse to_exp_signal (app/ops.py:241-251) into the iSTFT prologue */
+};
+
+int         gss_version(void);
+const char* gss_last_error(void);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t     gss_launch_count(void);
+
+/* FFT sizes this build has kernels for (writes up to `cap` entries, returns the count);
+ * hops N/2 (the reference's SciPy default), N/4 and N/8 are supported for each. */
+int         gss_supported_fft_sizes(int* sizes, int cap);
+
+/* Frame arithmetic of scipy.signal.stft(boundary='zeros', padded=True) as the
+ * reference calls it (main.py:97): nadd = (-n mod H) mod N, T = (n+nadd)/H + 1.
+ * Pure host function. */
+int gss_frame_count(int64_t n, int N, int H, int64_t* T, int64_t* nadd);
+
+/* A1+A2(+A3): replaces scipy.signal.stft(x, nperseg=N)[2] + utils.spectrum_to_feature
+ * (main.py:97-98, app/datasets/TIMIT/process.py:97-98) and optionally
+ * ops.to_log_signal (main.py:338).
+ *   wave [B, ld] f32 (first n samples of each row used) -> feat [B, T, N] f32. */
+int gss_stft_packed(const float* wave, int64_t B, int64_t n, int64_t ld, int N, int H,
+                    int flags, float eps, float* feat, void* stream);
+
+/* same, int16 PCM input as process.py:94 reads it (scipy gives complex64 there) */
+int gss_stft_packed_i16(const int16_t* wave, int64_t B, int64_t n, int64_t ld, int N, int H,
+                        int flags, float eps, float* feat, void* stream);
+
+/* (A5+)A6+A8: replaces utils.feature_to_spectrum + scipy.signal.istft(nperseg=N)
+ * (main.py:110-111), optionally preceded by ops.to_exp_signal (main.py:342).
+ *   feat [R, T, N] f32 -> wave_out [R, ld_out] f32, (T-1)*H samples per row. */
+int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H,
+                     int flags, float eps, float* wave_out, int64_t ld_out, void* stream);
+
+/* A1+A7+A8 fused synthesis stage (no reference code for A7):
+ * recompute the mixture spectrum from the waveform, multiply by the separator's
+ * per-source real gains and inverse-transform with register overlap-add.
+ *   wave [B, ld] f32, mask [B, S, T, N/2] f32 -> out [B*S, ld_out] f32, row b*S+s
+ *   (the output order of app/modules.py:396-399), (T-1)*H samples per row. */
+int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64_t n, int64_t ld,
+                   int N, int H, float* out, int64_t ld_out, void* stream);
+
+/* A7 alone on packed features: mix [B,T,N], mask [B,S,T,N/2] -> out [B*S,T,N] */
+int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_t T, int N,
+                   float* out, void* stream);
+
+/* A3 / A5: ops.to_log_signal / ops.to_exp_signal (app/ops.py:228-251) on `rows` rows of N */
+int gss_to_log(const float* in, float* out, int64_t rows, int N, float eps, void* stream);
+int gss_to_exp(const float* in, float* out, int64_t rows, int N, float eps, void* stream);
+
+/* A11: ops.batch_cross_snr (app/ops.py:191-225).  clear [B,m,L], noisy [B,n,L] ->
+ * snr [B,m,n]; batch_snr (ops.py:162-189) is the m=n=1 diagonal. */
+int gss_cross_snr(const float* clear, const float* noisy, int64_t B, int m, int n, int64_t L,
+                  float eps, float* snr, void* stream);
+
+/* A12: main.py:353-361.  sep [B,S,L], mix [B,L] -> partial[B] = sum_l (sum_s sep - mix)^2
+ * (the caller divides by B*L; per-utterance partials are what the ranks all-reduce). */
+int gss_ae_partial(const float* sep, const float* mix, int64_t B, int S, int64_t L,
+                   float* partial, void* stream);
+
+/* A9: main.py:112-116 WAV normalisation.  x [R, ld] f32 (len samples used) -> pcm [R, len]
+ * int16, each row shifted to its min and scaled to 32767 (truncation).
+ * minmax is a caller-provided scratch of 2*R floats. */
+int gss_wav16_normalise(const float* x, int64_t R, int64_t len, int64_t ld, float* minmax,
+                        int16_t* pcm, void* stream);
+
+/* ---- host-buffer entry points (what load_wavfile / save_wavfile bind to) ---- */
+
+/* main.py:67-99 minus file I/O: host wave [B,n] -> host feat [B,T,N] */
+int gss_stft_packed_host(const float* wave_h, int64_t B, int64_t n, int N, int H,
+                         int flags, float eps, float* feat_h);
+/* main.py:102-111 minus file I/O: host feat [R,T,N] -> host wave [R,(T-1)H] */
+int gss_istft_packed_host(const float* feat_h, int64_t R, int64_t T, int N, int H,
+                          int flags, float eps, float* wave_h);
+
+/* Chunked, double-buffered end-to-end helpers used by bench.py's e2e leg.
+ * gss_stft_h2d: pinned host wave -> device wave workspace (kept for the synthesis
+ *               stage) -> device feat; copies and kernels overlap chunk by chunk.
+ * gss_mask_istft_d2h: device wave + device mask -> device out workspace -> pinned host out.
+ * `chunks` >= 1 splits the batch; both return after the last copy has landed. */
+int gss_stft_h2d(const float* wave_h, float* wave_d, int64_t B, int64_t n, int64_t ld, int N, int H,
+                 int flags, float eps, float* feat_d, int chunks, void* stream);
+int gss_mask_istft_d2h(const float* wave_d, const float* mask_d, int64_t B, int S, int64_t n,
+                       int64_t ld, int N, int H, float* out_d, float* out_h, int64_t ld_out,
+                       int chunks, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSS_API_H */
