@@ -123,7 +123,7 @@ def _cpu_one(args):
     return 1
 
 
-def cpu_serial_baseline(budget_s=12.0, max_utts=256):
+def cpu_serial_baseline(budget_s=12.0, max_utts=4096):
     """1 core, serial per-utterance loop - how the reference drives SciPy
     (process.py:89, main.py:769-771)."""
     w = WORKLOAD
@@ -262,19 +262,21 @@ def run_native(args):
     # ---- e2e through the host-buffer API --------------------------------------
     pipe = SpectralPipeline(B, n, S, N, H, device=dev, chunks=8)
     pipe.wave_h.copy_(waves[0].cpu())
-    for i in range(max(2, min(args.warmup, 3))):
-        pipe.analyse()
-        pipe.synthesise(masks[i % NSETS])
     e2e_steps = max(3, min(args.steps, 10))
-    barrier()
-    te0 = torch.cuda.Event(enable_timing=True); te1 = torch.cuda.Event(enable_timing=True)
-    te0.record(stream)
-    for i in range(e2e_steps):
-        pipe.analyse()                       # pinned host waves -> device -> log features (separator input)
-        pipe.synthesise(masks[i % NSETS])    # masks (separator output, device) -> pinned host waveforms
-    te1.record(stream)
-    barrier()
-    e2e_ms = te0.elapsed_time(te1)
+    e2e_ms = float("nan")
+    if not args.no_e2e:
+        for i in range(max(2, min(args.warmup, 3))):
+            pipe.analyse()
+            pipe.synthesise(masks[i % NSETS])
+        barrier()
+        te0 = torch.cuda.Event(enable_timing=True); te1 = torch.cuda.Event(enable_timing=True)
+        te0.record(stream)
+        for i in range(e2e_steps):
+            pipe.analyse()                       # pinned host waves -> device -> log features (separator input)
+            pipe.synthesise(masks[i % NSETS])    # masks (separator output, device) -> pinned host waveforms
+        te1.record(stream)
+        barrier()
+        e2e_ms = te0.elapsed_time(te1)
 
     t = torch.tensor([total_ms, e2e_ms, stft_ms, synth_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -334,6 +336,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

@@ -29,9 +29,9 @@ REG_SCALE = 1e-2
 REG_TYPE = 'L2'
 
 USE_ASR = False
-SEPARATOR_TYPE = 'toy-v1'
-RECOGNIZER_TYPE = 'toy-v1'
-DISCRIMINATOR_TYPE = 'toy-v1'
+SEPARATOR_TYPE = 'toy'
+RECOGNIZER_TYPE = 'toy'
+DISCRIMINATOR_TYPE = 'toy'
 OPTIMIZER_TYPE = 'adam'
 LR = 1e-5
 LR_DECAY = None

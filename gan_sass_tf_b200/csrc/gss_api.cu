@@ -119,6 +119,7 @@ int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int 
     if (B == 0) return GSS_OK;
     gss::StftArgs<TIn> a{};
     a.wave = wave; a.feat = feat; a.B = B; a.n = n; a.ld = ld; a.eps = eps;
+    a.al_in = ((uintptr_t)wave % (2 * sizeof(TIn)) == 0) && (ld % 2 == 0 || B == 1);
     if (int rc = frame_count(n, N, H, &a.T, nullptr)) return rc;
     a.npairs = (int)((a.T + 1) / 2);
     cudaStream_t st = (cudaStream_t)stream;
@@ -146,7 +147,7 @@ int launch_istft(gss::IstftArgs a, cudaStream_t st) {
 template <int N, int HS, int ST>
 int launch_synth(gss::SynthArgs a, cudaStream_t st) {
     auto k = gss::mask_istft_kernel<N, HS, ST, WARPS>;
-    const size_t smem = team_smem<N>(WARPS);
+    const size_t smem = gss::SynthSmem<N, ST>::bytes(WARPS);
     if (int rc = prep(k, smem)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
     gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, smem));
@@ -231,6 +232,7 @@ int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H, int 
     if (R == 0) return GSS_OK;
     gss::IstftArgs a{};
     a.feat = feat; a.out = wave_out; a.rows = R; a.T = T; a.ld_out = ld_out; a.eps = eps;
+    a.al_out = ((uintptr_t)wave_out % 8 == 0) && (ld_out % 2 == 0 || R == 1);
     a.npairs = (int)((T + 1) / 2);
     cudaStream_t st = (cudaStream_t)stream;
     const bool ex = flags & GSS_FLAG_EXP;
@@ -249,6 +251,9 @@ int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64
     if (n < N) return fail(GSS_EUNSUPPORTED, "mask_istft: n=%lld < FFT_SIZE=%d", (long long)n, N);
     gss::SynthArgs a{};
     a.wave = wave; a.mask = mask; a.out = out; a.B = B; a.n = n; a.ld = ld; a.ld_out = ld_out; a.S = S;
+    if ((uintptr_t)mask % 16) return fail(GSS_EINVAL, "mask_istft: mask must be 16-byte aligned (TMA bulk copies)");
+    a.al_in = ((uintptr_t)wave % 8 == 0) && (ld % 2 == 0 || B == 1);
+    a.al_out = ((uintptr_t)out % 8 == 0) && (ld_out % 2 == 0 || B * S == 1);
     if (int rc = frame_count(n, N, H, &a.T, nullptr)) return rc;
     if (ld_out < (a.T - 1) * H) return fail(GSS_EINVAL, "mask_istft: ld_out=%lld < (T-1)*H=%lld", (long long)ld_out, (long long)((a.T - 1) * H));
     if (B == 0) return GSS_OK;

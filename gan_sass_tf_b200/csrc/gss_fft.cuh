@@ -169,32 +169,12 @@ __device__ __forceinline__ void team_init(TeamCtx<N>& c, int j, float* team_smem
     }
 }
 
-// thread-0 re-pairing so that (Z[i].x, Z[7-i].y) and (Z[i].y, Z[7-i].x) are always
-// (Z[k], Z[N-k]) pairs; see fft_model.fixup_thread0 / unfix_thread0.
-__device__ __forceinline__ void fixup_thread0(cv2 (&z)[8], bool t0) {
-    v2 r4 = z[4].re, r5 = z[5].re, r6 = z[6].re, r7 = z[7].re;
-    v2 i4 = z[4].im, i5 = z[5].im, i6 = z[6].im, i7 = z[7].im;
-    if (t0) {
-        z[4].re = make_float2(r4.y, r5.x); z[4].im = make_float2(i4.y, i5.x);
-        z[5].re = make_float2(r5.y, r6.x); z[5].im = make_float2(i5.y, i6.x);
-        z[6].re = make_float2(r6.y, r7.x); z[6].im = make_float2(i6.y, i7.x);
-        z[7].re = make_float2(r7.y, r4.x); z[7].im = make_float2(i7.y, i4.x);
-    }
-}
-__device__ __forceinline__ void unfix_thread0(cv2 (&z)[8], bool t0) {
-    v2 r4 = z[4].re, r5 = z[5].re, r6 = z[6].re, r7 = z[7].re;
-    v2 i4 = z[4].im, i5 = z[5].im, i6 = z[6].im, i7 = z[7].im;
-    if (t0) {   // A[4..7] = [B''7, B''4, B''5, B''6];  B[4..7] = A''[4..7]
-        z[4].re = make_float2(r7.y, r4.x); z[4].im = make_float2(i7.y, i4.x);
-        z[5].re = make_float2(r4.y, r5.x); z[5].im = make_float2(i4.y, i5.x);
-        z[6].re = make_float2(r5.y, r6.x); z[6].im = make_float2(i5.y, i6.x);
-        z[7].re = make_float2(r6.y, r7.x); z[7].im = make_float2(i6.y, i7.x);
-    }
-}
-
 // ---------------------------------------------------------------------------
 // forward: a[n0] (lanes e=0,1: samples 2j+e + L*n0; re = sequence a, im = sequence b)
-//       -> a[k2] (lanes A,B: Z[cA + L*k2], Z[cB + L*k2]) after the thread-0 fix-up.
+//       -> a[k2] (lanes A,B: Z[cA + L*k2], Z[cB + L*k2]).  Z[k] and Z[N-k] sit in the same
+//          thread: (A[i], B[7-i]) and (B[i], A[7-i]); thread 0 (columns 0 and L/2 pair with
+//          themselves): (A[i], A[8-i]), (A[0], A[4]) = (DC, Nyquist), (B[i], B[7-i]).
+//          gss_stream.cuh split_pair / pack_pair select the partner accordingly.
 template <int N>
 __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
     typedef Geo<N> G;
@@ -238,16 +218,14 @@ __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
         a[n2].im = make_float2(p[c.cA + G::E1_PLANE], p[c.cB + G::E1_PLANE]);
     }
     dft8<false>(a);
-    fixup_thread0(a, j == 0);
 }
 
-// inverse (unnormalised, e^{+...}): a[k2] in the fixed-up last-pass layout
+// inverse (unnormalised, e^{+...}): a[k2] in the last-pass layout above
 //       -> a[n0] (lanes e=0,1: samples 2j+e + L*n0; re/im = the two real sequences).
 template <int N>
 __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8]) {
     typedef Geo<N> G;
     const int j = c.j;
-    unfix_thread0(a, j == 0);
     team_sync();   // the previous transform's last read of the exchange buffers
     dft8<true>(a);
 #pragma unroll

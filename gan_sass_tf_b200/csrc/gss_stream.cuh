@@ -12,8 +12,11 @@
 //               written straight to global memory (no atomics, no shared
 //               memory round trip).
 //
-// Shared memory is used only for the two register exchanges inside each FFT
-// (gss_fft.cuh), private to the team, synchronised with __syncwarp.
+// Shared memory holds the two register exchanges inside each FFT (gss_fft.cuh),
+// private to the team and synchronised with __syncwarp, and - in the fused
+// synthesis kernel - a double-buffered stage for the separator's masks that a
+// single lane fills with 1-D TMA bulk copies (cp.async.bulk + mbarrier) one
+// frame pair ahead of the math.
 //
 // HS = H / L is the hop in slots: 1 (H = N/8), 2 (H = N/4), 4 (H = N/2, the
 // reference's SciPy default, main.py:97).  Positions are "padded" coordinates of
@@ -47,23 +50,30 @@ __device__ __forceinline__ float hann(int i) { return 0.5f - 0.5f * cospif(2.0f 
 // ---------------------------------------------------------------------------
 // sample access: the pair (p, p+1), p even, zero outside [0, n)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ v2 load_pair(const float* row, int64_t n, int64_t p, bool al) {
-    if (p >= 0 && p + 1 < n) {
-        if (al) return __ldg(reinterpret_cast<const float2*>(row + p));
-        return make_float2(__ldg(row + p), __ldg(row + p + 1));
-    }
-    v2 r = make_float2(0.f, 0.f);
-    if (p >= 0 && p < n) r.x = __ldg(row + p);
-    return r;
+__device__ __forceinline__ v2 load_pair_fast(const float* row, int64_t p, bool al) {
+    if (al) return __ldg(reinterpret_cast<const float2*>(row + p));
+    return make_float2(__ldg(row + p), __ldg(row + p + 1));
 }
-__device__ __forceinline__ v2 load_pair(const int16_t* row, int64_t n, int64_t p, bool al) {
-    if (p >= 0 && p + 1 < n) {
-        if (al) { short2 s = __ldg(reinterpret_cast<const short2*>(row + p)); return make_float2((float)s.x, (float)s.y); }
-        return make_float2((float)__ldg(row + p), (float)__ldg(row + p + 1));
-    }
+__device__ __forceinline__ v2 load_pair_fast(const int16_t* row, int64_t p, bool al) {
+    if (al) { short2 s = __ldg(reinterpret_cast<const short2*>(row + p)); return make_float2((float)s.x, (float)s.y); }
+    return make_float2((float)__ldg(row + p), (float)__ldg(row + p + 1));
+}
+template <typename TIn>
+__device__ __noinline__ v2 load_pair_edge(const TIn* row, int64_t n, int64_t p) {
     v2 r = make_float2(0.f, 0.f);
     if (p >= 0 && p < n) r.x = (float)__ldg(row + p);
+    if (p + 1 >= 0 && p + 1 < n) r.y = (float)__ldg(row + p + 1);
     return r;
+}
+// slots [sl, sl + CNT) of the padded signal; one range test for the whole group
+template <int L, int CNT, typename TIn>
+__device__ __forceinline__ void load_slots(const TIn* row, int64_t n, int64_t sl, int j, bool al, v2* dst) {
+    const bool inside = sl >= 4 && (sl + CNT - 4) * L <= n;
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) {
+        const int64_t p = (sl + i - 4) * L + 2 * j;
+        dst[i] = inside ? load_pair_fast(row, p, al) : load_pair_edge(row, n, p);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -77,6 +87,22 @@ __device__ __forceinline__ float exp_gain(float re, float im, float eps) {
     float a = sqrtf(fmaf(re, re, fmaf(im, im, eps)));
     return expm1f(a) / a;
 }
+// two bins at once, valid for a2 <= 1 (always true for waveforms in [-1, 1]: |X0| + |X_nyq| <= 1
+// and |X_k| <= 1 under scaling='spectrum'):  0.5*log1p(x) = atanh(s), s = x / (2 + x) <= 1/3,
+// atanh(s) = s * sum_k s^2k / (2k+1); truncated after k = 6 (next term < 1.5e-8 relative).
+__device__ __forceinline__ v2 log_gain2_small(v2 a2, float eps) {
+    v2 d = vadd(a2, vset(2.0f));
+    v2 s = vmul(a2, make_float2(__frcp_rn(d.x), __frcp_rn(d.y)));
+    v2 t = vmul(s, s);
+    v2 p = vfma(t, vset(1.0f / 13.0f), vset(1.0f / 11.0f));
+    p = vfma(p, t, vset(1.0f / 9.0f));
+    p = vfma(p, t, vset(1.0f / 7.0f));
+    p = vfma(p, t, vset(1.0f / 5.0f));
+    p = vfma(p, t, vset(1.0f / 3.0f));
+    p = vfma(p, t, vset(1.0f));
+    v2 e = vadd(a2, vset(eps));
+    return vmul(vmul(s, p), make_float2(rsqrtf(e.x), rsqrtf(e.y)));
+}
 
 // per-thread spectrum of a frame pair: bins k = c + L*i, lane x: c = cA, lane y: c = cB
 struct PairSpec {
@@ -84,18 +110,22 @@ struct PairSpec {
     v2 br[4], bi[4];   // frame b
 };
 
-// two-for-one split of the forward transform (window carries the 1/2 and 1/sum(w)).
+// Two-for-one split of the forward transform (the window carries the 1/2 and 1/sum(w)).
+// Partner of register i (bin k) is bin N-k: lanes crossed in register 7-i, except thread 0
+// whose two columns (0 and L/2) pair with themselves (see gss_fft.cuh fft_forward).
 template <int N>
 __device__ __forceinline__ void split_pair(const cv2 (&a)[8], bool t0, PairSpec& s) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+        const int rx = (i == 0) ? 4 : 8 - i;
         v2 pre = a[i].re, pim = a[i].im;
-        v2 qre = vswap(a[7 - i].re), qim = vswap(a[7 - i].im);
+        v2 qre = make_float2(t0 ? a[rx].re.x : a[7 - i].re.y, t0 ? a[7 - i].re.y : a[7 - i].re.x);
+        v2 qim = make_float2(t0 ? a[rx].im.x : a[7 - i].im.y, t0 ? a[7 - i].im.y : a[7 - i].im.x);
         s.ar[i] = vadd(pre, qre); s.ai[i] = vsub(pim, qim);
         s.br[i] = vadd(pim, qim); s.bi[i] = vsub(qre, pre);
-        if (i == 0 && t0) {   // lane x of thread 0 holds (Z[0], Z[N/2]): DC in "re", Nyquist in "im"
-            s.ar[0].x = 2.f * pre.x; s.ai[0].x = 2.f * qre.x;
-            s.br[0].x = 2.f * pim.x; s.bi[0].x = 2.f * qim.x;
+        if (i == 0) {   // lane x of thread 0 holds (Z[0], Z[N/2]): DC in "re", Nyquist in "im"
+            s.ar[0].x = t0 ? 2.f * pre.x : s.ar[0].x; s.ai[0].x = t0 ? 2.f * qre.x : s.ai[0].x;
+            s.br[0].x = t0 ? 2.f * pim.x : s.br[0].x; s.bi[0].x = t0 ? 2.f * qim.x : s.bi[0].x;
         }
     }
 }
@@ -104,16 +134,22 @@ __device__ __forceinline__ void split_pair(const cv2 (&a)[8], bool t0, PairSpec&
 template <int N>
 __device__ __forceinline__ void pack_pair(const v2 (&yar)[4], const v2 (&yai)[4], const v2 (&ybr)[4], const v2 (&ybi)[4],
                                           bool t0, cv2 (&a)[8]) {
+    v2 qre[4], qim[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         v2 pre = vsub(yar[i], ybi[i]), pim = vadd(yai[i], ybr[i]);
-        v2 qre = vadd(yar[i], ybi[i]), qim = vsub(ybr[i], yai[i]);
-        if (i == 0 && t0) {
-            pre.x = yar[0].x; pim.x = ybr[0].x;
-            qre.x = yai[0].x; qim.x = ybi[0].x;
+        qre[i] = vadd(yar[i], ybi[i]); qim[i] = vsub(ybr[i], yai[i]);
+        if (i == 0) {
+            pre.x = t0 ? yar[0].x : pre.x; pim.x = t0 ? ybr[0].x : pim.x;
+            qre[0].x = t0 ? yai[0].x : qre[0].x; qim[0].x = t0 ? ybi[0].x : qim[0].x;
         }
         a[i].re = pre; a[i].im = pim;
-        a[7 - i].re = vswap(qre); a[7 - i].im = vswap(qim);
+    }
+#pragma unroll
+    for (int r = 4; r < 8; ++r) {
+        const int ix = (r == 4) ? 0 : 8 - r;      // thread 0, lane x: the pair whose partner lives in register r
+        a[r].re = make_float2(t0 ? qre[ix].x : qre[7 - r].y, t0 ? qre[7 - r].y : qre[7 - r].x);
+        a[r].im = make_float2(t0 ? qim[ix].x : qim[7 - r].y, t0 ? qim[7 - r].y : qim[7 - r].x);
     }
 }
 
@@ -122,15 +158,13 @@ __device__ __forceinline__ void pack_pair(const v2 (&yar)[4], const v2 (&yai)[4]
 // ---------------------------------------------------------------------------
 template <class SG>
 struct OlaOut {
-    float* row;          // output row (sample 0 = padded position N/2)
     int64_t T;
     int j;
-    bool al;             // row is 8-byte aligned
+    bool al;             // rows are 8-byte aligned
     v2 invn[SG::HS];     // 1 / sum_t w^2 per slot residue (only when !CONST_NORM)
 
-    __device__ __forceinline__ void init(float* row_, int64_t T_, int j_) {
-        row = row_; T = T_; j = j_;
-        al = (reinterpret_cast<uintptr_t>(row_) & 7) == 0;
+    __device__ __forceinline__ void init(int64_t T_, int j_, bool al_) {
+        T = T_; j = j_; al = al_;
         if (!SG::CONST_NORM) {
 #pragma unroll
             for (int m = 0; m < SG::HS; ++m) {
@@ -145,7 +179,7 @@ struct OlaOut {
         }
     }
     // actual sum_t w^2[pp - tH] over the frames that exist (edges of the signal)
-    __device__ __forceinline__ float norm_at(int64_t sl, int e) const {
+    __device__ __noinline__ float norm_at(int64_t sl, int e) const {
         int64_t tlo = sl - 7; tlo = tlo <= 0 ? 0 : (tlo + SG::HS - 1) / SG::HS;
         int64_t thi = sl / SG::HS; if (thi > T - 1) thi = T - 1;
         float s = 0.f;
@@ -156,18 +190,23 @@ struct OlaOut {
         }
         return s > 1e-10f ? s : 1.0f;     // scipy.signal.istft: where(norm > 1e-10, norm, 1)
     }
-    __device__ __forceinline__ void write(int64_t sl, int m /* sl mod HS, static */, v2 v) const {
-        if (sl < 4 || sl >= 4 + (T - 1) * SG::HS) return;
-        if (SG::CONST_NORM) {
-            if (sl <= 7 - SG::HS || sl >= T * SG::HS) {       // fewer than R frames cover this slot
-                const float c = 0.375f * SG::R;
-                v.x *= c / norm_at(sl, 0); v.y *= c / norm_at(sl, 1);
-            }
-        } else {
-            v = vmul(v, invn[m]);
-        }
+    __device__ __forceinline__ void store(float* row, int64_t sl, v2 v) const {
         float* p = row + (sl - 4) * SG::L + 2 * j;
         if (al) *reinterpret_cast<float2*>(p) = v; else { p[0] = v.x; p[1] = v.y; }
+    }
+    // all ADV slots starting at `base` are inside the output and covered by R frames
+    __device__ __forceinline__ bool interior(int64_t base) const {
+        return base >= 8 - SG::HS && base >= 4 && base + SG::ADV <= (T - 1) * SG::HS + (SG::HS < 4 ? SG::HS : 4);
+    }
+    __device__ __forceinline__ void write(float* row, int64_t sl, int m /* sl mod HS, static */, v2 v, bool fast) const {
+        if (!SG::CONST_NORM) v = vmul(v, invn[m]);
+        if (fast) { store(row, sl, v); return; }
+        if (sl < 4 || sl >= 4 + (T - 1) * SG::HS) return;
+        if (SG::CONST_NORM && (sl <= 7 - SG::HS || sl >= T * SG::HS)) {   // fewer than R frames cover this slot
+            const float c = 0.375f * SG::R;
+            v.x *= c / norm_at(sl, 0); v.y *= c / norm_at(sl, 1);
+        }
+        store(row, sl, v);
     }
 };
 
@@ -182,6 +221,33 @@ __device__ __forceinline__ void make_window(int j, float scale, v2 (&w)[8]) {
 struct ChunkPlan { int ppc; int nchunk; };   // pairs per chunk, chunks per row
 
 // ---------------------------------------------------------------------------
+// 1-D TMA bulk copy + mbarrier (one lane issues, the whole team waits)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // STFT: wave [B, ld] -> packed feature [B, T, N] (+ to_log)      A1 + A2 (+ A3)
 // ---------------------------------------------------------------------------
 template <typename TIn>
@@ -189,6 +255,7 @@ struct StftArgs {
     const TIn* wave; float* feat;
     int64_t B, n, ld, T;
     int npairs, ppc, nchunk;
+    int al_in;                      // every row start is aligned for 2-sample vector loads
     float eps;
 };
 
@@ -205,6 +272,7 @@ __global__ void __launch_bounds__(WARPS * 32) stft_kernel(const StftArgs<TIn> p)
     const int64_t b = item / p.nchunk;
     const int c = (int)(item - b * p.nchunk);
     const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
+    const bool t0 = j == 0;
 
     TeamCtx<N> ctx;
     team_init<N>(ctx, j, smf + 4 * G::TW1_F4 + warp * G::TEAM_FLOATS, smem4);
@@ -212,46 +280,64 @@ __global__ void __launch_bounds__(WARPS * 32) stft_kernel(const StftArgs<TIn> p)
     make_window<SG>(j, 1.0f / (float)N, win);      // 1/sum(w) = 2/N, and the 1/2 of the two-for-one split
 
     const TIn* row = p.wave + b * p.ld;
-    const bool al = (reinterpret_cast<uintptr_t>(row) % (2 * sizeof(TIn))) == 0;
+    const bool al = p.al_in != 0;
     int64_t base = (int64_t)2 * q0 * HS;            // padded slot of ring[0]
-    auto ld_slot = [&](int64_t sl) { return load_pair(row, p.n, (sl - 4) * SG::L + 2 * j, al); };
 
     v2 ring[SG::RS], nxt[SG::ADV];
-#pragma unroll
-    for (int i = 0; i < SG::KEEP; ++i) ring[i] = ld_slot(base + i);
-#pragma unroll
-    for (int i = 0; i < SG::ADV; ++i) nxt[i] = ld_slot(base + SG::KEEP + i);
+    load_slots<SG::L, SG::KEEP>(row, p.n, base, j, al, ring);
+    load_slots<SG::L, SG::ADV>(row, p.n, base + SG::KEEP, j, al, nxt);
 
     for (int q = q0; q < q1; ++q) {
 #pragma unroll
         for (int i = 0; i < SG::ADV; ++i) ring[SG::KEEP + i] = nxt[i];
-        if (q + 1 < q1) {
-#pragma unroll
-            for (int i = 0; i < SG::ADV; ++i) nxt[i] = ld_slot(base + SG::RS + i);
-        }
+        if (q + 1 < q1) load_slots<SG::L, SG::ADV>(row, p.n, base + SG::RS, j, al, nxt);
         cv2 a[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], win[i]); a[i].im = vmul(ring[HS + i], win[i]); }
         fft_forward<N>(ctx, a);
         PairSpec s;
-        split_pair<N>(a, j == 0, s);
+        split_pair<N>(a, t0, s);
 
+        if (LOG) {
+            v2 a2a[4], a2b[4];
+            float mx = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a2a[i] = vfma(s.ar[i], s.ar[i], vmul(s.ai[i], s.ai[i]));
+                a2b[i] = vfma(s.br[i], s.br[i], vmul(s.bi[i], s.bi[i]));
+                mx = fmaxf(fmaxf(mx, fmaxf(a2a[i].x, a2a[i].y)), fmaxf(a2b[i].x, a2b[i].y));
+            }
+            if (__all_sync(0xffffffffu, mx <= 1.0f)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v2 ga = log_gain2_small(a2a[i], p.eps), gb = log_gain2_small(a2b[i], p.eps);
+                    s.ar[i] = vmul(s.ar[i], ga); s.ai[i] = vmul(s.ai[i], ga);
+                    s.br[i] = vmul(s.br[i], gb); s.bi[i] = vmul(s.bi[i], gb);
+                }
+            } else {            // large magnitudes (e.g. int16 PCM): libm-accurate path
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float g;
+                    g = log_gain(s.ar[i].x, s.ai[i].x, p.eps); s.ar[i].x *= g; s.ai[i].x *= g;
+                    g = log_gain(s.ar[i].y, s.ai[i].y, p.eps); s.ar[i].y *= g; s.ai[i].y *= g;
+                    g = log_gain(s.br[i].x, s.bi[i].x, p.eps); s.br[i].x *= g; s.bi[i].x *= g;
+                    g = log_gain(s.br[i].y, s.bi[i].y, p.eps); s.br[i].y *= g; s.bi[i].y *= g;
+                }
+            }
+        }
         const int64_t ta = 2 * (int64_t)q;
         float* ra = p.feat + (b * p.T + ta) * N;
         const bool hb = ta + 1 < p.T;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (LOG) {
-                float g;
-                g = log_gain(s.ar[i].x, s.ai[i].x, p.eps); s.ar[i].x *= g; s.ai[i].x *= g;
-                g = log_gain(s.ar[i].y, s.ai[i].y, p.eps); s.ar[i].y *= g; s.ai[i].y *= g;
-                g = log_gain(s.br[i].x, s.bi[i].x, p.eps); s.br[i].x *= g; s.bi[i].x *= g;
-                g = log_gain(s.br[i].y, s.bi[i].y, p.eps); s.br[i].y *= g; s.bi[i].y *= g;
-            }
             const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
             ra[kx] = s.ar[i].x; ra[N / 2 + kx] = s.ai[i].x;
             ra[ky] = s.ar[i].y; ra[N / 2 + ky] = s.ai[i].y;
-            if (hb) {
+        }
+        if (hb) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
                 ra[N + kx] = s.br[i].x; ra[N + N / 2 + kx] = s.bi[i].x;
                 ra[N + ky] = s.br[i].y; ra[N + N / 2 + ky] = s.bi[i].y;
             }
@@ -269,6 +355,7 @@ struct IstftArgs {
     const float* feat; float* out;
     int64_t rows, T, ld_out;
     int npairs, ppc, nchunk;
+    int al_out;
     float eps;
 };
 
@@ -286,6 +373,7 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     const int c = (int)(item - r * p.nchunk);
     const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
     const int qs = max(q0 - SG::HALO, 0);
+    const bool t0 = j == 0;
 
     TeamCtx<N> ctx;
     team_init<N>(ctx, j, smf + 4 * G::TW1_F4 + warp * G::TEAM_FLOATS, smem4);
@@ -293,7 +381,8 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     // frame = sum(w) * irfft = (N/2)(1/N) * raw inverse; interior 1/sum(w^2) folded in when constant
     make_window<SG>(j, SG::CONST_NORM ? 0.5f / (0.375f * SG::R) : 0.5f, win);
     OlaOut<SG> o;
-    o.init(p.out + r * p.ld_out, p.T, j);
+    o.init(p.T, j, p.al_out != 0);
+    float* orow = p.out + r * p.ld_out;
 
     v2 acc[SG::RS];
 #pragma unroll
@@ -326,7 +415,7 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
             }
         }
         cv2 a[8];
-        pack_pair<N>(yar, yai, ybr, ybi, j == 0, a);
+        pack_pair<N>(yar, yai, ybr, ybi, t0, a);
         fft_inverse<N>(ctx, a);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -334,8 +423,9 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
             acc[HS + i] = vfma(a[i].im, win[i], acc[HS + i]);
         }
         if (q >= q0) {
+            const bool fast = o.interior(base);
 #pragma unroll
-            for (int i = 0; i < SG::ADV; ++i) o.write(base + i, i % HS, acc[i]);
+            for (int i = 0; i < SG::ADV; ++i) o.write(orow, base + i, i % HS, acc[i], fast);
         }
 #pragma unroll
         for (int i = 0; i < SG::KEEP; ++i) acc[i] = acc[i + SG::ADV];
@@ -345,7 +435,7 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     }
     if (c == p.nchunk - 1) {
 #pragma unroll
-        for (int i = 0; i < SG::KEEP; ++i) o.write(base + i, i % HS, acc[i]);
+        for (int i = 0; i < SG::KEEP; ++i) o.write(orow, base + i, i % HS, acc[i], false);
     }
 }
 
@@ -354,22 +444,39 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
 // The mixture spectrum is recomputed from the waveform (4n bytes) instead of being
 // re-read (4TN bytes).  ST sources are carried per pass; S > ST runs as separate
 // items (source groups) that each recompute the forward transform.
+// Shared memory per team: FFT exchange + 2 stages x ST x 2 frames x N/2 mask gains.
 // ---------------------------------------------------------------------------
 struct SynthArgs {
     const float* wave; const float* mask; float* out;
     int64_t B, n, ld, T, ld_out;
     int S, ngroups;                 // ngroups = ceil(S / ST)
     int npairs, ppc, nchunk;
+    int al_in, al_out;
+};
+
+template <int N, int ST>
+struct SynthSmem {
+    static constexpr int NH = N / 2;
+    static constexpr int STAGE_FLOATS = ST * 2 * NH;              // per team, per stage
+    static constexpr int TEAM_FLOATS = Geo<N>::TEAM_FLOATS + 2 * STAGE_FLOATS;
+    static constexpr size_t bytes(int warps) {
+        return sizeof(float) * (4 * Geo<N>::TW1_F4 + (size_t)warps * TEAM_FLOATS) + sizeof(uint64_t) * 2 * warps;
+    }
 };
 
 template <int N, int HS, int ST, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs p) {
-    typedef SGeo<N, HS> SG; typedef Geo<N> G;
+    typedef SGeo<N, HS> SG; typedef Geo<N> G; typedef SynthSmem<N, ST> SM;
+    constexpr int NH = N / 2;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
-    fill_tw1<N>(smem4, threadIdx.x, WARPS * 32);
-    __syncthreads();
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
+    float* team = smf + 4 * G::TW1_F4 + warp * SM::TEAM_FLOATS;
+    float* stage = team + G::TEAM_FLOATS;                                  // 2 x STAGE_FLOATS, 16-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4 * G::TW1_F4 + WARPS * SM::TEAM_FLOATS) + 2 * warp;
+    fill_tw1<N>(smem4, threadIdx.x, WARPS * 32);
+    if (j == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
     const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t per_b = (int64_t)p.ngroups * p.nchunk;
     if (item >= p.B * per_b) return;
@@ -377,23 +484,36 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
     const int rem = (int)(item - b * per_b);
     const int grp = rem / p.nchunk, c = rem - grp * p.nchunk;
     const int s0 = grp * ST;
+    const int ns = min(ST, p.S - s0);                 // sources handled by this team
     const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
     const int qs = max(q0 - SG::HALO, 0);
+    const bool t0 = j == 0;
 
     TeamCtx<N> ctx;
-    team_init<N>(ctx, j, smf + 4 * G::TW1_F4 + warp * G::TEAM_FLOATS, smem4);
+    team_init<N>(ctx, j, team, smem4);
     v2 winf[8], wini[8];
     make_window<SG>(j, 1.0f / (float)N, winf);
     make_window<SG>(j, SG::CONST_NORM ? 0.5f / (0.375f * SG::R) : 0.5f, wini);
 
-    OlaOut<SG> o[ST];
-#pragma unroll
-    for (int s = 0; s < ST; ++s) o[s].init(p.out + (b * p.S + min(s0 + s, p.S - 1)) * p.ld_out, p.T, j);
+    OlaOut<SG> o;
+    o.init(p.T, j, p.al_out != 0);
+    float* orow0 = p.out + (b * p.S + s0) * p.ld_out;
+    const float* mrow0 = p.mask + ((b * p.S + s0) * p.T) * NH;       // source s: + s*T*NH; frame t: + t*NH
+
+    // one lane stages the masks of pair q into stage (q - qs) & 1
+    auto prefetch = [&](int q) {
+        if (j == 0) {
+            const int st = (q - qs) & 1;
+            const int64_t ta = 2 * (int64_t)q;
+            const uint32_t bytes = (ta + 1 < p.T ? 2 : 1) * NH * (uint32_t)sizeof(float);
+            mbar_expect_tx(&bars[st], bytes * ns);
+            for (int s = 0; s < ns; ++s)
+                tma_load_1d(stage + st * SM::STAGE_FLOATS + s * 2 * NH, mrow0 + ((int64_t)s * p.T + ta) * NH, bytes, &bars[st]);
+        }
+    };
 
     const float* row = p.wave + b * p.ld;
-    const bool al = (reinterpret_cast<uintptr_t>(row) & 7) == 0;
-    auto ld_slot = [&](int64_t sl) { return load_pair(row, p.n, (sl - 4) * SG::L + 2 * j, al); };
-    const int NH = N / 2;
+    const bool al = p.al_in != 0;
 
     v2 acc[ST][SG::RS];
 #pragma unroll
@@ -403,17 +523,17 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
 
     int64_t base = (int64_t)2 * qs * HS;
     v2 ring[SG::RS], nxt[SG::ADV];
-#pragma unroll
-    for (int i = 0; i < SG::KEEP; ++i) ring[i] = ld_slot(base + i);
-#pragma unroll
-    for (int i = 0; i < SG::ADV; ++i) nxt[i] = ld_slot(base + SG::KEEP + i);
+    prefetch(qs);
+    load_slots<SG::L, SG::KEEP>(row, p.n, base, j, al, ring);
+    load_slots<SG::L, SG::ADV>(row, p.n, base + SG::KEEP, j, al, nxt);
 
     for (int q = qs; q < q1; ++q) {
 #pragma unroll
         for (int i = 0; i < SG::ADV; ++i) ring[SG::KEEP + i] = nxt[i];
         if (q + 1 < q1) {
-#pragma unroll
-            for (int i = 0; i < SG::ADV; ++i) nxt[i] = ld_slot(base + SG::RS + i);
+            // the other stage was last read in iteration q-1; every lane has passed a __syncwarp since
+            prefetch(q + 1);
+            load_slots<SG::L, SG::ADV>(row, p.n, base + SG::RS, j, al, nxt);
         }
         PairSpec x;
         {
@@ -421,25 +541,29 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], winf[i]); a[i].im = vmul(ring[HS + i], winf[i]); }
             fft_forward<N>(ctx, a);
-            split_pair<N>(a, j == 0, x);
+            split_pair<N>(a, t0, x);
         }
         const int64_t ta = 2 * (int64_t)q;
         const bool hb = ta + 1 < p.T;
+        const int stg = (q - qs) & 1;
+        mbar_wait(&bars[stg], ((q - qs) >> 1) & 1);
+        const float* mst = stage + stg * SM::STAGE_FLOATS;
+        const bool fast = q >= q0 && o.interior(base);
 #pragma unroll
         for (int s = 0; s < ST; ++s) {
-            if (s0 + s < p.S) {
-                const float* ma = p.mask + (((b * p.S + s0 + s) * p.T) + ta) * NH;
+            if (s < ns) {
+                const float* ma = mst + s * 2 * NH;
                 v2 yar[4], yai[4], ybr[4], ybi[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
-                    v2 ga = make_float2(__ldg(ma + kx), __ldg(ma + ky));
-                    v2 gb = hb ? make_float2(__ldg(ma + NH + kx), __ldg(ma + NH + ky)) : make_float2(0.f, 0.f);
+                    v2 ga = make_float2(ma[kx], ma[ky]);
+                    v2 gb = hb ? make_float2(ma[NH + kx], ma[NH + ky]) : make_float2(0.f, 0.f);
                     yar[i] = vmul(x.ar[i], ga); yai[i] = vmul(x.ai[i], ga);
                     ybr[i] = vmul(x.br[i], gb); ybi[i] = vmul(x.bi[i], gb);
                 }
                 cv2 a[8];
-                pack_pair<N>(yar, yai, ybr, ybi, j == 0, a);
+                pack_pair<N>(yar, yai, ybr, ybi, t0, a);
                 fft_inverse<N>(ctx, a);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -447,8 +571,9 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
                     acc[s][HS + i] = vfma(a[i].im, wini[i], acc[s][HS + i]);
                 }
                 if (q >= q0) {
+                    float* orow = orow0 + s * p.ld_out;
 #pragma unroll
-                    for (int i = 0; i < SG::ADV; ++i) o[s].write(base + i, i % HS, acc[s][i]);
+                    for (int i = 0; i < SG::ADV; ++i) o.write(orow, base + i, i % HS, acc[s][i], fast);
                 }
 #pragma unroll
                 for (int i = 0; i < SG::KEEP; ++i) acc[s][i] = acc[s][i + SG::ADV];
@@ -463,9 +588,9 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
     if (c == p.nchunk - 1) {
 #pragma unroll
         for (int s = 0; s < ST; ++s)
-            if (s0 + s < p.S) {
+            if (s < ns) {
 #pragma unroll
-                for (int i = 0; i < SG::KEEP; ++i) o[s].write(base + i, i % HS, acc[s][i]);
+                for (int i = 0; i < SG::KEEP; ++i) o.write(orow0 + s * p.ld_out, base + i, i % HS, acc[s][i], false);
             }
     }
 }

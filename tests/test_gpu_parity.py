@@ -279,7 +279,7 @@ def test_log_exp_golden(T, ops, golden):
             hparams.FFT_SIZE = N
             f = g[f"logexp_{N}/f"]
             lg = ops.to_log_signal(dev(T, f)).cpu().numpy()
-            ex = ops.to_exp_signal(dev(T, f)).cpu().numpy()
+            ex = ops.to_exp_signal(dev(T, f * np.float32(0.3))).cpu().numpy()   # make_golden.py:143
             assert R.rel_l2(lg, g[f"logexp_{N}/to_log"]) < 1e-6
             assert R.rel_l2(ex, g[f"logexp_{N}/to_exp"]) < 1e-6
             el = ops.to_exp_signal(ops.to_log_signal(dev(T, f))).cpu().numpy()

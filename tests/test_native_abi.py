@@ -1,0 +1,72 @@
+"""CPU-side checks of the drop-in boundary: libgss.so builds in-tree, loads, exports
+every symbol include/gss_api.h declares, and rejects bad arguments without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    from gan_sass_tf_b200 import build, _native
+    build.build()
+    _native.lib()
+    return _native
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gss_api.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gss_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(native):
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    h = ctypes.CDLL(native.LIB_PATH)
+    for s in syms:
+        assert hasattr(h, s), f"{s} declared in include/gss_api.h but not exported by libgss.so"
+    # and the ctypes table binds exactly the declared surface
+    assert sorted(native.SIGNATURES) == syms
+
+
+def test_version_and_sizes(native):
+    assert native.lib().gss_version() >= 100
+    sizes = native.supported_fft_sizes()
+    assert 512 in sizes and all(s & (s - 1) == 0 for s in sizes)
+
+
+@pytest.mark.parametrize("n,N,H,T,nadd", [
+    (48000, 256, 128, 376, 0), (48000, 512, 128, 376, 0), (46797, 512, 128, 367, 51), (64000, 512, 128, 501, 0),
+    (960000, 1024, 256, 3751, 0), (48000, 4096, 1024, 48, 128), (48000, 256, 64, 751, 0),
+])
+def test_frame_count_k1(native, n, N, H, T, nadd):
+    from oracle import ref_oracle as R
+    assert native.frame_count(n, N, H) == (T, nadd) == R.frame_count(n, N, H)
+
+
+def test_argument_errors_without_gpu(native):
+    lib = native.lib()
+    with pytest.raises(ValueError):
+        native.frame_count(0, 512, 128)
+    # bad FFT size / hop / null pointers are rejected before any CUDA call
+    assert lib.gss_stft_packed(None, 1, 4000, 4000, 500, 125, 0, 1e-7, None, None) == native.GSS_EUNSUPPORTED
+    assert b"power of two" in lib.gss_last_error()
+    assert lib.gss_stft_packed(None, 1, 4000, 4000, 512, 100, 0, 1e-7, None, None) == native.GSS_EUNSUPPORTED
+    assert lib.gss_stft_packed(None, 1, 4000, 4000, 512, 128, 0, 1e-7, None, None) == native.GSS_EINVAL
+    assert lib.gss_istft_packed(None, 1, 10, 512, 128, 0, 1e-7, None, 1152, None) == native.GSS_EINVAL
+    assert lib.gss_mask_istft(None, None, 1, 3, 4000, 4000, 512, 128, None, 4096, None) == native.GSS_EINVAL
+    with pytest.raises(ValueError):
+        native.check(native.GSS_EINVAL)
+
+
+def test_ops_reject_cpu_tensors(native):
+    import torch
+    from gan_sass_tf_b200.app import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.stft(torch.zeros(1, 4000), 512, 128)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.to_log_signal(torch.zeros(1, 4, 256))
