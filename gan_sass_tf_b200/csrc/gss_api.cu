@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -88,7 +89,7 @@ int64_t team_slots(K kernel, int warps, size_t smem) {
 constexpr int WARPS = 4;
 
 template <int N>
-size_t team_smem(int warps) { return sizeof(float) * (4 * gss::Geo<N>::TW1_F4 + (size_t)warps * gss::Geo<N>::TEAM_FLOATS); }
+size_t team_smem(int warps) { return sizeof(float) * ((size_t)warps * gss::Geo<N>::TEAM_FLOATS); }
 
 template <typename K>
 int prep(K kernel, size_t smem) {
@@ -97,8 +98,8 @@ int prep(K kernel, size_t smem) {
 }
 
 // ---- STFT ---------------------------------------------------------------
-template <int N, int HS, bool LOG, typename TIn>
-int launch_stft(gss::StftArgs<TIn> a, cudaStream_t st) {
+template <int N, int HS, bool LOG, typename TIn, int WARPS = 4>
+int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
     auto k = gss::stft_kernel<N, HS, LOG, TIn, WARPS>;
     const size_t smem = team_smem<N>(WARPS);
     if (int rc = prep(k, smem)) return rc;
@@ -107,6 +108,24 @@ int launch_stft(gss::StftArgs<TIn> a, cudaStream_t st) {
     int64_t items = a.B * a.nchunk;
     k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
     return after_launch("stft_kernel");
+}
+int tune(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+template <int N, int HS, bool LOG, typename TIn>
+int launch_stft(gss::StftArgs<TIn> a, cudaStream_t st) {
+#ifdef GSS_TUNE
+    if (N == 512 && HS == 2 && LOG && sizeof(TIn) == 4) {
+        switch (tune("GSS_STFT_WARPS", 4)) {
+            case 12: return launch_stft_w<512, 2, true, TIn, 12>(a, st);
+            case 14: return launch_stft_w<512, 2, true, TIn, 14>(a, st);
+            case 16: return launch_stft_w<512, 2, true, TIn, 16>(a, st);
+            default: break;
+        }
+    }
+#endif
+    return launch_stft_w<N, HS, LOG, TIn, 4>(a, st);
 }
 template <typename TIn>
 int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps, float* feat, void* stream) {
@@ -144,17 +163,54 @@ int launch_istft(gss::IstftArgs a, cudaStream_t st) {
 }
 
 // ---- fused synthesis ------------------------------------------------------
-template <int N, int HS, int ST>
-int launch_synth(gss::SynthArgs a, cudaStream_t st) {
+template <int N, int HS, int ST, int WARPS = 4>
+int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
     auto k = gss::mask_istft_kernel<N, HS, ST, WARPS>;
     const size_t smem = gss::SynthSmem<N, ST>::bytes(WARPS);
     if (int rc = prep(k, smem)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
+    { static int stg = -1; if (stg < 0) { const char* v = getenv("GSS_STAGGER"); stg = v ? atoi(v) : 0; } a.stagger = stg; }
+#ifdef GSS_TIMING
+    static long long* tbuf = nullptr;
+    if (!tbuf) cudaMalloc(&tbuf, sizeof(long long) * 8 * 65536);
+    a.timing = tbuf;
+#endif
     gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.B * a.ngroups * a.nchunk;
     k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
+#ifdef GSS_TIMING
+    {
+        static int calls = 0;
+        if (++calls == 8) {     // after warm-up: dump the per-phase cycle split of this launch
+            cudaStreamSynchronize(st);
+            int64_t n = items < 65536 ? items : 65536;
+            std::string buf(sizeof(long long) * 8 * n, 0);
+            cudaMemcpy(&buf[0], tbuf, buf.size(), cudaMemcpyDeviceToHost);
+            const long long* t = (const long long*)buf.data();
+            double s[8] = {0}; for (int64_t i = 0; i < n; ++i) for (int k = 0; k < 8; ++k) s[k] += t[i * 8 + k];
+            fprintf(stderr, "[gss timing] items %lld pairs/item %.1f | cycles per pair: fwd %.0f maskwait %.0f mask+pack %.0f inv %.0f ola+store %.0f looptop %.0f | total %.0f\n",
+                    (long long)n, s[6] / n, s[0] / s[6], s[1] / s[6], s[2] / s[6], s[3] / s[6], s[4] / s[6], s[7] / s[6],
+                    (s[0] + s[1] + s[2] + s[3] + s[4] + s[7]) / s[6]);
+        }
+    }
+#endif
     return after_launch("mask_istft_kernel");
+}
+template <int N, int HS, int ST>
+int launch_synth(gss::SynthArgs a, cudaStream_t st) {
+#ifdef GSS_TUNE
+    if (N == 512 && HS == 2 && ST == 3) {
+        switch (tune("GSS_SYNTH_WARPS", 4)) {
+            case 9: return launch_synth_w<512, 2, 3, 9>(a, st);
+            case 10: return launch_synth_w<512, 2, 3, 10>(a, st);
+            case 11: return launch_synth_w<512, 2, 3, 11>(a, st);
+            case 12: return launch_synth_w<512, 2, 3, 12>(a, st);
+            default: break;
+        }
+    }
+#endif
+    return launch_synth_w<N, HS, ST, 4>(a, st);
 }
 template <int N, int HS>
 int synth_by_s(gss::SynthArgs a, cudaStream_t st) {

@@ -115,12 +115,12 @@ struct Geo {
     static constexpr int M = N / 64;          // middle radix
     static constexpr int TPF = N / 16;        // threads per transform
     static constexpr int L = N / 8;
-    static constexpr int P0 = TPF + 4;        // E0 pitch, float4 units
+    static constexpr int P0 = TPF + 4;        // E0 pitch, v2 units (re plane, im plane at +E0_PLANE)
     static constexpr int P1 = L + 4;          // E1 pitch, floats
-    static constexpr int E0_F4 = 8 * P0;      // float4 count
+    static constexpr int E0_PLANE = 8 * P0;   // v2 per plane
+    static constexpr int E0_F4 = 8 * P0;      // float4-equivalents (both planes)
     static constexpr int E1_PLANE = 8 * P1;   // floats per plane
     static constexpr int TEAM_FLOATS = E0_F4 * 4 + 2 * E1_PLANE;
-    static constexpr int TW1_F4 = 4 * (M + 1);   // middle twiddles, [q][k1] padded, float4 (re0,re1,im0,im1)
     static_assert(M == 8, "this round implements N = 512 (M = 8); 256/1024 are wired in fft_model.py only");
 };
 
@@ -129,36 +129,41 @@ template <int N>
 struct TeamCtx {
     int j;            // thread index inside the team
     int cA, cB;       // last-pass butterflies
-    float4* e0;       // team exchange buffer 0
+    v2* e0;           // team exchange buffer 0 (two planes of v2)
     float* e1;        // team exchange buffer 1 (re plane, im plane at +E1_PLANE)
-    const float4* tw1;  // CTA-shared middle twiddle table
     cv2 tw0[8];       // pass-0 twiddles W_N^{(2j+e)*k0}, k0 = 1..7 ([0] unused)
+    cv2 tw1[3];       // middle twiddles W_L^{(2q+e)*k1} for k1 = 1, 2, 4, q = j % 4
 };
+
+// the seven twiddles w^1..w^7 from the stored w^1, w^2, w^4 (4 complex products)
+__device__ __forceinline__ void expand_tw(const cv2 (&b)[3], cv2 (&w)[8]) {
+    w[1] = b[0]; w[2] = b[1]; w[4] = b[2];
+    w[3] = cmul<false>(b[0], b[1]);
+    w[5] = cmul<false>(b[0], b[2]);
+    w[6] = cmul<false>(b[1], b[2]);
+    w[7] = cmul<false>(w[3], b[2]);
+}
 
 __device__ __forceinline__ void team_sync() { __syncwarp(); }
 
-// fill the CTA-shared middle-twiddle table: entry [q*(M+1) + k1] = W_L^{(2q+e)*k1}
 template <int N>
-__device__ __forceinline__ void fill_tw1(float4* tw1, int tid, int nthreads) {
-    typedef Geo<N> G;
-    for (int i = tid; i < 4 * G::M; i += nthreads) {
-        int q = i / G::M, k1 = i % G::M;
-        float s0, c0, s1, c1;
-        sincospif(-2.0f * (float)((2 * q) * k1) / (float)G::L, &s0, &c0);
-        sincospif(-2.0f * (float)((2 * q + 1) * k1) / (float)G::L, &s1, &c1);
-        tw1[q * (G::M + 1) + k1] = make_float4(c0, c1, s0, s1);
-    }
-}
-
-template <int N>
-__device__ __forceinline__ void team_init(TeamCtx<N>& c, int j, float* team_smem, const float4* tw1) {
+__device__ __forceinline__ void team_init(TeamCtx<N>& c, int j, float* team_smem) {
     typedef Geo<N> G;
     c.j = j;
     c.cA = j ? j : 0;
     c.cB = j ? G::L - j : G::L / 2;
-    c.e0 = reinterpret_cast<float4*>(team_smem);
+    c.e0 = reinterpret_cast<v2*>(team_smem);
     c.e1 = team_smem + G::E0_F4 * 4;
-    c.tw1 = tw1;
+    const int q = j & 3;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const int k = 1 << b;
+        float s0, c0, s1, c1;
+        sincospif(-2.0f * (float)((2 * q) * k) / (float)G::L, &s0, &c0);
+        sincospif(-2.0f * (float)((2 * q + 1) * k) / (float)G::L, &s1, &c1);
+        c.tw1[b].re = make_float2(c0, c1);
+        c.tw1[b].im = make_float2(s0, s1);
+    }
 #pragma unroll
     for (int k0 = 1; k0 < 8; ++k0) {
         float s0, c0, s1, c1;
@@ -181,31 +186,32 @@ __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
     const int j = c.j;
     team_sync();   // the previous transform's last read of the exchange buffers
     dft8<false>(a);
-    c.e0[j] = make_float4(a[0].re.x, a[0].re.y, a[0].im.x, a[0].im.y);
+    c.e0[j] = a[0].re; c.e0[G::E0_PLANE + j] = a[0].im;
+    {
 #pragma unroll
-    for (int k0 = 1; k0 < 8; ++k0) {
-        cv2 t = cmul<false>(a[k0], c.tw0[k0]);
-        c.e0[k0 * G::P0 + j] = make_float4(t.re.x, t.re.y, t.im.x, t.im.y);
+        for (int k0 = 1; k0 < 8; ++k0) {
+            cv2 t = cmul<false>(a[k0], c.tw0[k0]);
+            c.e0[k0 * G::P0 + j] = t.re; c.e0[G::E0_PLANE + k0 * G::P0 + j] = t.im;
+        }
     }
     team_sync();
     {   // middle (M = 8): thread (k0 = j/4, q = j%4), lanes n2 = 2q+e
         const int k0 = j >> 2, q = j & 3;
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
-            float4 v = c.e0[k0 * G::P0 + 4 * n1 + q];
-            a[n1].re = make_float2(v.x, v.y);
-            a[n1].im = make_float2(v.z, v.w);
+            a[n1].re = c.e0[k0 * G::P0 + 4 * n1 + q];
+            a[n1].im = c.e0[G::E0_PLANE + k0 * G::P0 + 4 * n1 + q];
         }
         dft8<false>(a);
         float* re0 = c.e1 + (2 * q) * G::P1 + k0;
         float* re1 = re0 + G::P1;
         re0[0] = a[0].re.x; re1[0] = a[0].re.y;
         re0[G::E1_PLANE] = a[0].im.x; re1[G::E1_PLANE] = a[0].im.y;
+        cv2 w[8];
+        expand_tw(c.tw1, w);
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) {
-            float4 w = c.tw1[q * (G::M + 1) + k1];
-            cv2 tw; tw.re = make_float2(w.x, w.y); tw.im = make_float2(w.z, w.w);
-            cv2 t = cmul<false>(a[k1], tw);
+            cv2 t = cmul<false>(a[k1], w[k1]);
             re0[8 * k1] = t.re.x; re1[8 * k1] = t.re.y;
             re0[8 * k1 + G::E1_PLANE] = t.im.x; re1[8 * k1 + G::E1_PLANE] = t.im.y;
         }
@@ -241,28 +247,26 @@ __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8]) {
         const float* re1 = re0 + G::P1;
         a[0].re = make_float2(re0[0], re1[0]);
         a[0].im = make_float2(re0[G::E1_PLANE], re1[G::E1_PLANE]);
+        cv2 w[8];
+        expand_tw(c.tw1, w);
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) {
             cv2 t;
             t.re = make_float2(re0[8 * k1], re1[8 * k1]);
             t.im = make_float2(re0[8 * k1 + G::E1_PLANE], re1[8 * k1 + G::E1_PLANE]);
-            float4 w = c.tw1[q * (G::M + 1) + k1];
-            cv2 tw; tw.re = make_float2(w.x, w.y); tw.im = make_float2(w.z, w.w);
-            a[k1] = cmul<true>(t, tw);
+            a[k1] = cmul<true>(t, w[k1]);
         }
         dft8<true>(a);
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1)
-            c.e0[k0 * G::P0 + 4 * n1 + q] = make_float4(a[n1].re.x, a[n1].re.y, a[n1].im.x, a[n1].im.y);
+        { c.e0[k0 * G::P0 + 4 * n1 + q] = a[n1].re; c.e0[G::E0_PLANE + k0 * G::P0 + 4 * n1 + q] = a[n1].im; }
     }
     team_sync();
     {
-        float4 v = c.e0[j];
-        a[0].re = make_float2(v.x, v.y); a[0].im = make_float2(v.z, v.w);
+        a[0].re = c.e0[j]; a[0].im = c.e0[G::E0_PLANE + j];
 #pragma unroll
         for (int k0 = 1; k0 < 8; ++k0) {
-            v = c.e0[k0 * G::P0 + j];
-            cv2 t; t.re = make_float2(v.x, v.y); t.im = make_float2(v.z, v.w);
+            cv2 t; t.re = c.e0[k0 * G::P0 + j]; t.im = c.e0[G::E0_PLANE + k0 * G::P0 + j];
             a[k0] = cmul<true>(t, c.tw0[k0]);
         }
     }

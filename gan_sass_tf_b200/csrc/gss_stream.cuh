@@ -161,10 +161,14 @@ struct OlaOut {
     int64_t T;
     int j;
     bool al;             // rows are 8-byte aligned
-    v2 invn[SG::HS];     // 1 / sum_t w^2 per slot residue (only when !CONST_NORM)
+    float oscale;        // kScale x (1 / gain the caller's window carries)
+    v2 invn[SG::HS];     // oscale / sum_t w^2 per slot residue (only when !CONST_NORM)
+    // sum(w)/N = 1/2 and, when it is constant, the interior 1/sum(w^2)
+    static constexpr float kScale = SG::CONST_NORM ? 0.5f / (0.375f * SG::R) : 0.5f;
 
-    __device__ __forceinline__ void init(int64_t T_, int j_, bool al_) {
+    __device__ __forceinline__ void init(int64_t T_, int j_, bool al_, float win_gain) {
         T = T_; j = j_; al = al_;
+        oscale = kScale * win_gain;
         if (!SG::CONST_NORM) {
 #pragma unroll
             for (int m = 0; m < SG::HS; ++m) {
@@ -174,7 +178,7 @@ struct OlaOut {
                     float w1 = hann<SG::N>(m * SG::L + 2 * j + 1 + r * SG::H);
                     s0 += w0 * w0; s1 += w1 * w1;
                 }
-                invn[m] = make_float2(1.f / s0, 1.f / s1);
+                invn[m] = make_float2(oscale / s0, oscale / s1);
             }
         }
     }
@@ -198,8 +202,10 @@ struct OlaOut {
     __device__ __forceinline__ bool interior(int64_t base) const {
         return base >= 8 - SG::HS && base >= 4 && base + SG::ADV <= (T - 1) * SG::HS + (SG::HS < 4 ? SG::HS : 4);
     }
+    // v is the raw overlap-add of hann * (unnormalised inverse transform); `scale` = sum(w)/N
+    // (= 1/2) and, when constant, the interior 1/sum(w^2)
     __device__ __forceinline__ void write(float* row, int64_t sl, int m /* sl mod HS, static */, v2 v, bool fast) const {
-        if (!SG::CONST_NORM) v = vmul(v, invn[m]);
+        v = vmul(v, SG::CONST_NORM ? vset(oscale) : invn[m]);
         if (fast) { store(row, sl, v); return; }
         if (sl < 4 || sl >= 4 + (T - 1) * SG::HS) return;
         if (SG::CONST_NORM && (sl <= 7 - SG::HS || sl >= T * SG::HS)) {   // fewer than R frames cover this slot
@@ -260,12 +266,10 @@ struct StftArgs {
 };
 
 template <int N, int HS, bool LOG, typename TIn, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) stft_kernel(const StftArgs<TIn> p) {
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((65536 / (WARPS * 32)) / 8) * 8) stft_kernel(const StftArgs<TIn> p) {
     typedef SGeo<N, HS> SG; typedef Geo<N> G;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
-    fill_tw1<N>(smem4, threadIdx.x, WARPS * 32);
-    __syncthreads();
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
     const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
     if (item >= p.B * p.nchunk) return;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(WARPS * 32) stft_kernel(const StftArgs<TIn> p)
     const bool t0 = j == 0;
 
     TeamCtx<N> ctx;
-    team_init<N>(ctx, j, smf + 4 * G::TW1_F4 + warp * G::TEAM_FLOATS, smem4);
+    team_init<N>(ctx, j, smf + warp * G::TEAM_FLOATS);
     v2 win[8];
     make_window<SG>(j, 1.0f / (float)N, win);      // 1/sum(w) = 2/N, and the 1/2 of the two-for-one split
 
@@ -364,8 +368,6 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     typedef SGeo<N, HS> SG; typedef Geo<N> G;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
-    fill_tw1<N>(smem4, threadIdx.x, WARPS * 32);
-    __syncthreads();
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
     const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
     if (item >= p.rows * p.nchunk) return;
@@ -376,12 +378,12 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     const bool t0 = j == 0;
 
     TeamCtx<N> ctx;
-    team_init<N>(ctx, j, smf + 4 * G::TW1_F4 + warp * G::TEAM_FLOATS, smem4);
+    team_init<N>(ctx, j, smf + warp * G::TEAM_FLOATS);
     v2 win[8];
-    // frame = sum(w) * irfft = (N/2)(1/N) * raw inverse; interior 1/sum(w^2) folded in when constant
-    make_window<SG>(j, SG::CONST_NORM ? 0.5f / (0.375f * SG::R) : 0.5f, win);
+    // frame = sum(w) * irfft = (N/2)(1/N) * raw inverse: the 1/2 and 1/sum(w^2) are applied at the store
+    make_window<SG>(j, 1.0f, win);
     OlaOut<SG> o;
-    o.init(p.T, j, p.al_out != 0);
+    o.init(p.T, j, p.al_out != 0, 1.0f);
     float* orow = p.out + r * p.ld_out;
 
     v2 acc[SG::RS];
@@ -446,8 +448,15 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
 // items (source groups) that each recompute the forward transform.
 // Shared memory per team: FFT exchange + 2 stages x ST x 2 frames x N/2 mask gains.
 // ---------------------------------------------------------------------------
+#ifdef GSS_TIMING
+#define GSS_T(k) do { long long t_ = clock64(); if (j == 0) tacc[k] += t_ - tprev; tprev = t_; } while (0)
+#else
+#define GSS_T(k) do { } while (0)
+#endif
 struct SynthArgs {
     const float* wave; const float* mask; float* out;
+    long long* timing;              // [items][8] cycle accumulators (GSS_TIMING builds only)
+    int stagger;                    // start skew in cycles between co-resident teams (0 = none)
     int64_t B, n, ld, T, ld_out;
     int S, ngroups;                 // ngroups = ceil(S / ST)
     int npairs, ppc, nchunk;
@@ -460,21 +469,20 @@ struct SynthSmem {
     static constexpr int STAGE_FLOATS = ST * 2 * NH;              // per team, per stage
     static constexpr int TEAM_FLOATS = Geo<N>::TEAM_FLOATS + 2 * STAGE_FLOATS;
     static constexpr size_t bytes(int warps) {
-        return sizeof(float) * (4 * Geo<N>::TW1_F4 + (size_t)warps * TEAM_FLOATS) + sizeof(uint64_t) * 2 * warps;
+        return sizeof(float) * ((size_t)warps * TEAM_FLOATS) + sizeof(uint64_t) * 2 * warps;
     }
 };
 
 template <int N, int HS, int ST, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs p) {
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((65536 / (WARPS * 32)) / 8) * 8) mask_istft_kernel(const SynthArgs p) {
     typedef SGeo<N, HS> SG; typedef Geo<N> G; typedef SynthSmem<N, ST> SM;
     constexpr int NH = N / 2;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
-    float* team = smf + 4 * G::TW1_F4 + warp * SM::TEAM_FLOATS;
+    float* team = smf + warp * SM::TEAM_FLOATS;
     float* stage = team + G::TEAM_FLOATS;                                  // 2 x STAGE_FLOATS, 16-byte aligned
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4 * G::TW1_F4 + WARPS * SM::TEAM_FLOATS) + 2 * warp;
-    fill_tw1<N>(smem4, threadIdx.x, WARPS * 32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smf + WARPS * SM::TEAM_FLOATS) + 2 * warp;
     if (j == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
     const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
@@ -489,14 +497,17 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
     const int qs = max(q0 - SG::HALO, 0);
     const bool t0 = j == 0;
 
+    if (p.stagger > 0) {     // de-phase the teams that share an SM sub-partition (they run identical code)
+        const long long tgo = clock64() + (long long)(blockIdx.x & 3) * p.stagger;
+        while (clock64() < tgo) { }
+    }
     TeamCtx<N> ctx;
-    team_init<N>(ctx, j, team, smem4);
-    v2 winf[8], wini[8];
-    make_window<SG>(j, 1.0f / (float)N, winf);
-    make_window<SG>(j, SG::CONST_NORM ? 0.5f / (0.375f * SG::R) : 0.5f, wini);
+    team_init<N>(ctx, j, team);
+    v2 win[8];                                     // hann / N: analysis scale; synthesis rescaled at the store
+    make_window<SG>(j, 1.0f / (float)N, win);
 
     OlaOut<SG> o;
-    o.init(p.T, j, p.al_out != 0);
+    o.init(p.T, j, p.al_out != 0, (float)N);
     float* orow0 = p.out + (b * p.S + s0) * p.ld_out;
     const float* mrow0 = p.mask + ((b * p.S + s0) * p.T) * NH;       // source s: + s*T*NH; frame t: + t*NH
 
@@ -515,11 +526,14 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
     const float* row = p.wave + b * p.ld;
     const bool al = p.al_in != 0;
 
-    v2 acc[ST][SG::RS];
+    // overlap-add state carried between pairs: KEEP slots per source.  The source loop is a
+    // real loop (one copy of the inverse transform in the instruction stream); the
+    // accumulators rotate through acc[0] so that indexing stays static.
+    v2 acc[ST][SG::KEEP];
 #pragma unroll
     for (int s = 0; s < ST; ++s)
 #pragma unroll
-        for (int i = 0; i < SG::RS; ++i) acc[s][i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < SG::KEEP; ++i) acc[s][i] = make_float2(0.f, 0.f);
 
     int64_t base = (int64_t)2 * qs * HS;
     v2 ring[SG::RS], nxt[SG::ADV];
@@ -527,7 +541,11 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
     load_slots<SG::L, SG::KEEP>(row, p.n, base, j, al, ring);
     load_slots<SG::L, SG::ADV>(row, p.n, base + SG::KEEP, j, al, nxt);
 
+#ifdef GSS_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
     for (int q = qs; q < q1; ++q) {
+        GSS_T(7);
 #pragma unroll
         for (int i = 0; i < SG::ADV; ++i) ring[SG::KEEP + i] = nxt[i];
         if (q + 1 < q1) {
@@ -539,17 +557,20 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
         {
             cv2 a[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], winf[i]); a[i].im = vmul(ring[HS + i], winf[i]); }
+            for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], win[i]); a[i].im = vmul(ring[HS + i], win[i]); }
             fft_forward<N>(ctx, a);
             split_pair<N>(a, t0, x);
         }
+        GSS_T(0);
         const int64_t ta = 2 * (int64_t)q;
         const bool hb = ta + 1 < p.T;
         const int stg = (q - qs) & 1;
         mbar_wait(&bars[stg], ((q - qs) >> 1) & 1);
+        GSS_T(1);
         const float* mst = stage + stg * SM::STAGE_FLOATS;
-        const bool fast = q >= q0 && o.interior(base);
-#pragma unroll
+        const bool own = q >= q0;
+        const bool fast = own && o.interior(base);
+#pragma unroll 1
         for (int s = 0; s < ST; ++s) {
             if (s < ns) {
                 const float* ma = mst + s * 2 * NH;
@@ -564,21 +585,34 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
                 }
                 cv2 a[8];
                 pack_pair<N>(yar, yai, ybr, ybi, t0, a);
+                GSS_T(2);
                 fft_inverse<N>(ctx, a);
+                GSS_T(3);
+                v2 cur[SG::RS];
+#pragma unroll
+                for (int i = 0; i < SG::RS; ++i) cur[i] = i < SG::KEEP ? acc[0][i] : make_float2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    acc[s][i] = vfma(a[i].re, wini[i], acc[s][i]);
-                    acc[s][HS + i] = vfma(a[i].im, wini[i], acc[s][HS + i]);
+                    cur[i] = vfma(a[i].re, win[i], cur[i]);
+                    cur[HS + i] = vfma(a[i].im, win[i], cur[HS + i]);
                 }
-                if (q >= q0) {
+                if (own) {
                     float* orow = orow0 + s * p.ld_out;
 #pragma unroll
-                    for (int i = 0; i < SG::ADV; ++i) o.write(orow, base + i, i % HS, acc[s][i], fast);
+                    for (int i = 0; i < SG::ADV; ++i) o.write(orow, base + i, i % HS, cur[i], fast);
                 }
 #pragma unroll
-                for (int i = 0; i < SG::KEEP; ++i) acc[s][i] = acc[s][i + SG::ADV];
+                for (int i = 0; i < SG::KEEP; ++i) acc[0][i] = cur[i + SG::ADV];
+                GSS_T(4);
+            }
+            if (ST > 1) {            // rotate: acc[0] <- acc[1] <- ... <- acc[ST-1] <- acc[0]
 #pragma unroll
-                for (int i = SG::KEEP; i < SG::RS; ++i) acc[s][i] = make_float2(0.f, 0.f);
+                for (int i = 0; i < SG::KEEP; ++i) {
+                    v2 t = acc[0][i];
+#pragma unroll
+                    for (int k = 0; k + 1 < ST; ++k) acc[k][i] = acc[k + 1][i];
+                    acc[ST - 1][i] = t;
+                }
             }
         }
 #pragma unroll
@@ -593,6 +627,12 @@ __global__ void __launch_bounds__(WARPS * 32) mask_istft_kernel(const SynthArgs 
                 for (int i = 0; i < SG::KEEP; ++i) o.write(orow0 + s * p.ld_out, base + i, i % HS, acc[s][i], false);
             }
     }
+#ifdef GSS_TIMING
+    if (j == 0 && p.timing) {
+        tacc[6] = q1 - qs;
+        for (int k = 0; k < 8; ++k) p.timing[item * 8 + k] = tacc[k];
+    }
+#endif
 }
 
 }  // namespace gss

@@ -1,0 +1,47 @@
+"""Per-kernel timings at the C2 shape (B=256, n=48000, N=512, H=128): device time per launch,
+rotating inputs.  Usage: python tools/kbench.py [N H B n]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gan_sass_tf_b200.app import ops
+from gan_sass_tf_b200 import _native
+
+N, H, B, n = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 else (512, 128, 256, 48000)
+T, _ = _native.frame_count(n, N, H)
+dev = torch.device("cuda")
+g = torch.Generator(device=dev).manual_seed(0)
+waves = [(torch.randn(B, n, device=dev, generator=g) * 0.1).clamp_(-1, 1) for _ in range(3)]
+
+
+def timeit(name, fn, bytes_, reps=20):
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{name:28s} {ms * 1e3:8.1f} us   {bytes_ / ms / 1e6:7.0f} GB/s   ({B * T / 2 / ms / 1e3:.1f} M pairs/s)")
+
+
+feat = [ops.stft(w, N, H) for w in waves]
+timeit("stft", lambda i: ops.stft(waves[i % 3], N, H), 4 * B * (n + T * N))
+timeit("stft_log", lambda i: ops.stft_log(waves[i % 3], N, H), 4 * B * (n + T * N))
+timeit("istft", lambda i: ops.istft(feat[i % 3], H), 4 * B * (T * N + (T - 1) * H))
+timeit("istft_exp", lambda i: ops.istft(feat[i % 3], H, exp=True), 4 * B * (T * N + (T - 1) * H))
+for S in (1, 2, 3, 4):
+    masks = [torch.rand(B, S, T, N // 2, device=dev, generator=g) for _ in range(3)]
+    out = torch.empty(B * S, (T - 1) * H, device=dev)
+    timeit(f"mask_istft S={S}", lambda i: ops.mask_istft(waves[i % 3], masks[i % 3], N, H, out=out),
+           4 * B * (n + S * T * N // 2 + S * (T - 1) * H))
+    del masks
+x = feat[0]
+from gan_sass_tf_b200.app import hparams
+hparams.FFT_SIZE = N
+timeit("to_log", lambda i: ops.to_log_signal(feat[i % 3]), 8 * B * T * N)
+timeit("to_exp", lambda i: ops.to_exp_signal(feat[i % 3]), 8 * B * T * N)
+m3 = torch.rand(B, 3, T, N // 2, device=dev, generator=g)
+timeit("apply_mask S=3", lambda i: ops.apply_mask(feat[i % 3], m3), 4 * B * T * N * (1 + 1.5 + 3))
