@@ -22,6 +22,7 @@ SIGNATURES = {
     "gss_version": (c_int, []),
     "gss_last_error": (c_char_p, []),
     "gss_launch_count": (c_int64, []),
+    "gss_set_path": (c_int, [c_int]),
     "gss_supported_fft_sizes": (c_int, [POINTER(c_int), c_int]),
     "gss_frame_count": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "gss_stft_packed": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P]),
@@ -86,6 +87,11 @@ def supported_fft_sizes():
     buf = (c_int * 16)()
     k = lib().gss_supported_fft_sizes(buf, 16)
     return tuple(buf[i] for i in range(min(k, 16)))
+
+
+def set_path(path: int):
+    """0 = automatic kernel selection, 1 = any-size shared-memory kernels only."""
+    check(lib().gss_set_path(path))
 
 
 def launch_count() -> int:

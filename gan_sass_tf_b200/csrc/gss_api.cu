@@ -12,6 +12,7 @@
 
 #include "../../include/gss_api.h"
 #include "gss_elem.cuh"
+#include "gss_generic.cuh"
 #include "gss_stream.cuh"
 
 namespace {
@@ -45,11 +46,13 @@ int sm_count() {
     return sms[dev];
 }
 
-bool supported_n(int N) { return N == 512; }
+std::atomic<int> g_force_generic{0};
+bool fast_n(int N) { return N == 512 && !g_force_generic.load(std::memory_order_relaxed); }   // register-streaming kernels
+bool supported_n(int N) { return N >= 64 && N <= 4096 && !(N & (N - 1)); }  // the rest: shared-memory FFT
 
 int check_nh(int N, int H, int* hs) {
     if (N < 16 || (N & (N - 1))) return fail(GSS_EUNSUPPORTED, "FFT_SIZE %d is not a power of two", N);
-    if (!supported_n(N)) return fail(GSS_EUNSUPPORTED, "FFT_SIZE %d not supported by this build (512)", N);
+    if (!supported_n(N)) return fail(GSS_EUNSUPPORTED, "FFT_SIZE %d outside the supported range 64..4096", N);
     if (H * 2 == N) *hs = 4; else if (H * 4 == N) *hs = 2; else if (H * 8 == N) *hs = 1;
     else return fail(GSS_EUNSUPPORTED, "hop %d must be N/2, N/4 or N/8 (N=%d)", H, N);
     return GSS_OK;
@@ -97,6 +100,40 @@ int prep(K kernel, size_t smem) {
     return GSS_OK;
 }
 
+// ---- any-size path (gss_generic.cuh) -------------------------------------------
+template <typename TIn>
+int launch_stft_generic(const TIn* wave, int64_t B, int64_t n, int64_t ld, int64_t T, int N, int H, int flags, float eps,
+                        float* feat, cudaStream_t st) {
+    gss::gen::StftArgs a{};
+    a.wave = wave; a.feat = feat; a.B = B; a.n = n; a.ld = ld; a.T = T; a.N = N; a.H = H;
+    a.log = (flags & GSS_FLAG_LOG) ? 1 : 0; a.eps = eps;
+    // enough CTAs for ~4 waves, at least 4 frames per CTA to amortise the twiddle table
+    int64_t fpc = (B * T + (int64_t)sm_count() * 16 - 1) / ((int64_t)sm_count() * 16);
+    a.fpc = (int)(fpc < 4 ? 4 : (fpc > 64 ? 64 : fpc));
+    const size_t smem = sizeof(float2) * 3 * (N / 2);
+    auto k = gss::gen::stft_kernel<TIn>;
+    if (int rc = prep(k, smem)) return rc;
+    if (B > 65535) return fail(GSS_EUNSUPPORTED, "generic stft: B=%lld > 65535 rows per launch", (long long)B);
+    dim3 grid((unsigned)((T + a.fpc - 1) / a.fpc), (unsigned)B);
+    k<<<grid, gss::gen::THREADS, smem, st>>>(a);
+    return after_launch("gen::stft_kernel");
+}
+
+template <bool FROM_WAVE>
+int launch_ola_generic(gss::gen::OlaArgs a, cudaStream_t st) {
+    const int R = a.N / a.H;
+    a.ft = 8;
+    const int span = (a.ft + R - 1) * a.H + a.N;
+    const size_t smem = sizeof(float2) * 3 * (a.N / 2) + sizeof(float) * 2 * span;
+    auto k = gss::gen::ola_kernel<FROM_WAVE>;
+    if (int rc = prep(k, smem)) return rc;
+    if (a.rows > 65535) return fail(GSS_EUNSUPPORTED, "generic istft: %lld rows > 65535 per launch", (long long)a.rows);
+    const int64_t hops = (a.T - 1) + R / 2;
+    dim3 grid((unsigned)((hops + a.ft - 1) / a.ft), (unsigned)a.rows);
+    k<<<grid, gss::gen::THREADS, smem, st>>>(a);
+    return after_launch("gen::ola_kernel");
+}
+
 // ---- STFT ---------------------------------------------------------------
 template <int N, int HS, bool LOG, typename TIn, int WARPS = 4>
 int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
@@ -142,6 +179,7 @@ int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int 
     if (int rc = frame_count(n, N, H, &a.T, nullptr)) return rc;
     a.npairs = (int)((a.T + 1) / 2);
     cudaStream_t st = (cudaStream_t)stream;
+    if (!fast_n(N)) return launch_stft_generic<TIn>(wave, B, n, ld, a.T, N, H, flags, eps, feat, st);
     const bool lg = flags & GSS_FLAG_LOG;
 #define GSS_CASE(NN, HH) if (N == NN && hs == HH) return lg ? launch_stft<NN, HH, true, TIn>(a, st) : launch_stft<NN, HH, false, TIn>(a, st);
     GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
@@ -263,6 +301,11 @@ extern "C" {
 int gss_version(void) { return 100; }
 const char* gss_last_error(void) { return g_err.c_str(); }
 int64_t gss_launch_count(void) { return g_launches.load(); }
+int gss_set_path(int path) {
+    if (path != 0 && path != 1) return fail(GSS_EINVAL, "set_path: 0 = automatic, 1 = any-size shared-memory kernels only");
+    g_force_generic.store(path);
+    return GSS_OK;
+}
 int gss_supported_fft_sizes(int* sizes, int cap) {
     int k = 0;
     for (int N = 16; N <= 65536; N *= 2)
@@ -291,6 +334,12 @@ int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H, int 
     a.al_out = ((uintptr_t)wave_out % 8 == 0) && (ld_out % 2 == 0 || R == 1);
     a.npairs = (int)((T + 1) / 2);
     cudaStream_t st = (cudaStream_t)stream;
+    if (!fast_n(N)) {
+        gss::gen::OlaArgs g{};
+        g.feat = feat; g.out = wave_out; g.rows = R; g.T = T; g.ld_out = ld_out; g.N = N; g.H = H; g.S = 1;
+        g.exp = (flags & GSS_FLAG_EXP) ? 1 : 0; g.eps = eps;
+        return launch_ola_generic<false>(g, st);
+    }
     const bool ex = flags & GSS_FLAG_EXP;
 #define GSS_CASE(NN, HH) if (N == NN && hs == HH) return ex ? launch_istft<NN, HH, true>(a, st) : launch_istft<NN, HH, false>(a, st);
     GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
@@ -315,6 +364,12 @@ int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64
     if (B == 0) return GSS_OK;
     a.npairs = (int)((a.T + 1) / 2);
     cudaStream_t st = (cudaStream_t)stream;
+    if (!fast_n(N)) {
+        gss::gen::OlaArgs g{};
+        g.wave = wave; g.mask = mask; g.out = out; g.rows = B * S; g.n = n; g.ld = ld; g.T = a.T; g.ld_out = ld_out;
+        g.N = N; g.H = H; g.S = S;
+        return launch_ola_generic<true>(g, st);
+    }
 #define GSS_CASE(NN, HH) if (N == NN && hs == HH) return synth_by_s<NN, HH>(a, st);
     GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
 #undef GSS_CASE

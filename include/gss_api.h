@@ -47,6 +47,11 @@ const char* gss_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t     gss_launch_count(void);
 
+/* Kernel selection: 0 = automatic (register-streaming kernels where the FFT size has them, the
+ * any-size shared-memory kernels otherwise), 1 = any-size kernels only.  Process-wide; meant for
+ * cross-checking the two implementations against each other. */
+int         gss_set_path(int path);
+
 /* FFT sizes this build has kernels for (writes up to `cap` entries, returns the count);
  * hops N/2 (the reference's SciPy default), N/4 and N/8 are supported for each. */
 int         gss_supported_fft_sizes(int* sizes, int cap);

@@ -222,6 +222,27 @@ def test_apply_mask_matches_oracle(T, ops):
     assert np.array_equal(out, R.apply_mask(mix, mask))       # one multiply per element: bit-exact
 
 
+def test_streaming_and_generic_paths_agree(T, ops):
+    """N = 512 has two independent implementations (register-streaming FFT, shared-memory
+    Stockham FFT): same inputs, results within float32 rounding of each other."""
+    from gan_sass_tf_b200 import _native
+    N, H, n, B, S = 512, 128, 9000, 3, 3
+    rng = np.random.default_rng(77)
+    x = dev(T, speechish(rng, B, n))
+    Tn, _ = R.frame_count(n, N, H)
+    m = dev(T, rng.random((B, S, Tn, N // 2)).astype(np.float32))
+    fast = (ops.stft(x, N, H), ops.stft_log(x, N, H), ops.mask_istft(x, m, N, H))
+    fast += (ops.istft(fast[0], H),)
+    try:
+        _native.set_path(1)
+        slow = (ops.stft(x, N, H), ops.stft_log(x, N, H), ops.mask_istft(x, m, N, H))
+        slow += (ops.istft(fast[0], H),)
+    finally:
+        _native.set_path(0)
+    for a, b in zip(fast, slow):
+        assert R.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+
+
 # --------------------------------------------------------------------------
 # full-size configs: properties that do not need the oracle at full size
 # --------------------------------------------------------------------------
