@@ -278,6 +278,16 @@ def run_native(args):
         barrier()
         e2e_ms = te0.elapsed_time(te1)
 
+    # ---- untimed full-size property check + the metric all-reduce (the only collective) ----
+    from gan_sass_tf_b200.app import parallel
+    nchk = 16
+    mk = masks[0][:nchk] + 0.05
+    mk = (mk / mk.sum(dim=1, keepdim=True)).contiguous()
+    rec = ops.mask_istft(waves[0][:nchk].contiguous(), mk, N, H).reshape(nchk, S, -1).sum(dim=1)[:, :n]
+    snr = ops.batch_snr(waves[0][:nchk].contiguous(), rec.contiguous())          # dB per utterance
+    vec = parallel.metric_vector(float(snr.sum()), 0.0, float(snr.sum()), float(nchk), device=dev)
+    recon_snr_db, _, _, checked = parallel.allreduce_metrics(vec)
+
     t = torch.tensor([total_ms, e2e_ms, stft_ms, synth_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -319,6 +329,8 @@ def run_native(args):
                     "api": "SpectralPipeline.analyse/synthesise -> gss_stft_h2d / gss_mask_istft_d2h (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "check": {"recon_snr_db": recon_snr_db, "utterances": int(checked),
+                      "what": "sum_s iSTFT(mask_s * STFT(x)) vs x with sum_s mask_s = 1, mean over ranks (NCCL all-reduce)"},
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_serial_baseline()
