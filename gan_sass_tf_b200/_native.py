@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgss.so")
+# GSS_LIB: developer override (instrumented / tuning builds); the product path is the in-tree library
+LIB_PATH = os.environ.get("GSS_LIB") or os.path.join(_HERE, "lib", "libgss.so")
 
 GSS_OK, GSS_EINVAL, GSS_EUNSUPPORTED, GSS_ECUDA, GSS_ENOMEM = 0, -1, -2, -3, -4
 FLAG_LOG, FLAG_EXP = 1, 2

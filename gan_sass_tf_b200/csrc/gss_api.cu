@@ -204,7 +204,10 @@ int launch_istft(gss::IstftArgs a, cudaStream_t st) {
 template <int N, int HS, int ST, int WARPS = 4>
 int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
     auto k = gss::mask_istft_kernel<N, HS, ST, WARPS>;
-    const size_t smem = gss::SynthSmem<N, ST>::bytes(WARPS);
+    size_t smem = gss::SynthSmem<N, ST>::bytes(WARPS);
+#ifdef GSS_TUNE
+    smem += (size_t)tune("GSS_EXTRA_SMEM", 0);      // occupancy limiter for single-warp-per-SMSP experiments
+#endif
     if (int rc = prep(k, smem)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
     { static int stg = -1; if (stg < 0) { const char* v = getenv("GSS_STAGGER"); stg = v ? atoi(v) : 0; } a.stagger = stg; }
