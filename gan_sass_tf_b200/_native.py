@@ -40,6 +40,9 @@ SIGNATURES = {
     "gss_istft_packed_host": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P]),
     "gss_stft_h2d": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int, _P]),
     "gss_mask_istft_d2h": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, _P, _P, c_int64, c_int, _P]),
+    "gss_stft_h2d_async": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int, _P]),
+    "gss_mask_istft_d2h_async": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, _P, _P, c_int64, c_int, _P]),
+    "gss_wait_host": (c_int, [_P]),
 }
 
 _lib = None

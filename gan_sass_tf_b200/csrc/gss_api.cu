@@ -283,16 +283,43 @@ struct Workspace {
 std::mutex g_ws_mu;
 Workspace g_ws_in, g_ws_out;
 
+// Copy engines of the host-buffer pipelines.  One H2D and one D2H stream per host thread, so that
+// uploads of batch k+1 and downloads of batch k use both directions of the link at once.
+// Buffers with a download in flight are remembered (device source, host destination) so that a later
+// call can order itself after that copy without a host-side synchronisation.
 struct CopyStreams {
+    static constexpr int NTAG = 8;
+    struct Tag { const void* key = nullptr; cudaEvent_t ev = nullptr; };
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t order = nullptr;
+    Tag src[NTAG], dst[NTAG];       // out_d buffers being read by a D2H copy / out_h buffers being written
     bool ok = false;
     int init() {
         if (ok) return GSS_OK;
         CK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
         for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&order, cudaEventDisableTiming));
+        for (auto& t : src) CK(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+        for (auto& t : dst) CK(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
         ok = true; return GSS_OK;
+    }
+    static Tag* find(Tag* tags, const void* key) {
+        for (int i = 0; i < NTAG; ++i) if (tags[i].key == key) return &tags[i];
+        return nullptr;
+    }
+    // slot for `key`; when the table is full every pending download is drained first
+    int claim(Tag* tags, const void* key, Tag** out) {
+        Tag* t = find(tags, key);
+        if (!t) t = find(tags, nullptr);
+        if (!t) {
+            CK(cudaStreamSynchronize(d2h));
+            for (int i = 0; i < NTAG; ++i) { src[i].key = nullptr; dst[i].key = nullptr; }
+            t = &tags[0];
+        }
+        t->key = key; *out = t;
+        return GSS_OK;
     }
 };
 thread_local CopyStreams g_cs;
@@ -463,15 +490,20 @@ int gss_istft_packed_host(const float* feat_h, int64_t R, int64_t T, int N, int 
     return GSS_OK;
 }
 
-// Chunked pipelines: chunk k's copy overlaps chunk k-1's kernel.
-int gss_stft_h2d(const float* wave_h, float* wave_d, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps,
-                 float* feat_d, int chunks, void* stream) {
+// Chunked pipelines: chunk k's copy overlaps chunk k-1's kernel.  The *_async forms only enqueue
+// (uploads on the library's H2D stream, kernels on the caller's stream, downloads on the library's
+// D2H stream) and return; gss_wait_host() blocks until a download into a host buffer has landed.
+int gss_stft_h2d_async(const float* wave_h, float* wave_d, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps,
+                       float* feat_d, int chunks, void* stream) {
     int64_t T = 0;
     if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
     if (!wave_h || !wave_d || !feat_d) return fail(GSS_EINVAL, "stft_h2d: null pointer");
     if (chunks < 1 || ld < n) return fail(GSS_EINVAL, "stft_h2d: bad chunks/ld");
     if (int rc = g_cs.init()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    // the upload may overwrite a wave_d that kernels already enqueued on `stream` still read
+    CK(cudaEventRecord(g_cs.order, st));
+    CK(cudaStreamWaitEvent(g_cs.h2d, g_cs.order, 0));
     const int64_t per = (B + chunks - 1) / chunks;
     int k = 0;
     for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
@@ -483,18 +515,26 @@ int gss_stft_h2d(const float* wave_h, float* wave_d, int64_t B, int64_t n, int64
         CK(cudaStreamWaitEvent(st, ev, 0));
         if (int rc = gss_stft_packed(wave_d + b0 * ld, nb, n, ld, N, H, flags, eps, feat_d + b0 * T * N, stream)) return rc;
     }
-    CK(cudaStreamSynchronize(st));
     return GSS_OK;
 }
 
-int gss_mask_istft_d2h(const float* wave_d, const float* mask_d, int64_t B, int S, int64_t n, int64_t ld, int N, int H,
-                       float* out_d, float* out_h, int64_t ld_out, int chunks, void* stream) {
+int gss_stft_h2d(const float* wave_h, float* wave_d, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps,
+                 float* feat_d, int chunks, void* stream) {
+    if (int rc = gss_stft_h2d_async(wave_h, wave_d, B, n, ld, N, H, flags, eps, feat_d, chunks, stream)) return rc;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return GSS_OK;
+}
+
+int gss_mask_istft_d2h_async(const float* wave_d, const float* mask_d, int64_t B, int S, int64_t n, int64_t ld, int N, int H,
+                             float* out_d, float* out_h, int64_t ld_out, int chunks, void* stream) {
     int64_t T = 0;
     if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
     if (!out_h || !out_d) return fail(GSS_EINVAL, "mask_istft_d2h: null pointer");
     if (chunks < 1) return fail(GSS_EINVAL, "mask_istft_d2h: bad chunks");
     if (int rc = g_cs.init()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    // a download that still reads this out_d (an earlier batch through the same workspace) goes first
+    if (CopyStreams::Tag* t = CopyStreams::find(g_cs.src, out_d)) CK(cudaStreamWaitEvent(st, t->ev, 0));
     const int64_t len = (T - 1) * H;
     const int64_t per = (B + chunks - 1) / chunks;
     int k = 0;
@@ -508,8 +548,25 @@ int gss_mask_istft_d2h(const float* wave_d, const float* mask_d, int64_t B, int 
         CK(cudaMemcpy2DAsync(out_h + b0 * S * len, sizeof(float) * len, out_d + b0 * S * ld_out, sizeof(float) * ld_out,
                              sizeof(float) * len, nb * S, cudaMemcpyDeviceToHost, g_cs.d2h));
     }
-    CK(cudaStreamSynchronize(g_cs.d2h));
+    CopyStreams::Tag* ts = nullptr; CopyStreams::Tag* td = nullptr;
+    if (int rc = g_cs.claim(g_cs.src, out_d, &ts)) return rc;
+    if (int rc = g_cs.claim(g_cs.dst, out_h, &td)) return rc;
+    CK(cudaEventRecord(ts->ev, g_cs.d2h));
+    CK(cudaEventRecord(td->ev, g_cs.d2h));
     return GSS_OK;
+}
+
+int gss_wait_host(const void* host_ptr) {
+    if (!g_cs.ok) return GSS_OK;
+    if (!host_ptr) { CK(cudaStreamSynchronize(g_cs.d2h)); return GSS_OK; }     // every pending download
+    if (CopyStreams::Tag* t = CopyStreams::find(g_cs.dst, host_ptr)) CK(cudaEventSynchronize(t->ev));
+    return GSS_OK;
+}
+
+int gss_mask_istft_d2h(const float* wave_d, const float* mask_d, int64_t B, int S, int64_t n, int64_t ld, int N, int H,
+                       float* out_d, float* out_h, int64_t ld_out, int chunks, void* stream) {
+    if (int rc = gss_mask_istft_d2h_async(wave_d, mask_d, B, S, n, ld, N, H, out_d, out_h, ld_out, chunks, stream)) return rc;
+    return gss_wait_host(out_h);
 }
 
 }  // extern "C"

@@ -23,7 +23,12 @@
 // scipy.signal.stft(boundary='zeros'): padded index pp = p + N/2.
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 #include "gss_fft.cuh"
+
+#ifndef GSS_ROLL_SOURCES
+#define GSS_ROLL_SOURCES 1
+#endif
 
 namespace gss {
 
@@ -248,9 +253,62 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// one lane of the (converged) warp, chosen by the hardware: lets the compiler keep the bulk-copy
+// operands in uniform registers instead of looping over the active lanes
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Loop structure shared by the streaming kernels.  A run of pairs [qs, q1) is walked in
+// three stretches: slow [qs, qa) - fast [qa, qb) - slow [qb, q1).  The fast body has no
+// bounds checks, no edge normalisation and aligned 64-bit global accesses through running
+// pointers; the slow body is the fully general one (signal edges, ragged tails, unaligned
+// rows, halo pairs).  Both are instances of one generic lambda, so they share all state.
+// ---------------------------------------------------------------------------
+struct FastTag { static constexpr bool value = true; };
+struct SlowTag { static constexpr bool value = false; };
+
+template <int L, int CNT>
+__device__ __forceinline__ void load_slots_fast(const float* p, v2* dst) {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) dst[i] = __ldg(reinterpret_cast<const float2*>(p + i * L));
+}
+template <int L, int CNT>
+__device__ __forceinline__ void load_slots_fast(const int16_t* p, v2* dst) {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) { short2 s = __ldg(reinterpret_cast<const short2*>(p + i * L)); dst[i] = make_float2((float)s.x, (float)s.y); }
+}
+
+// last pair index q (inclusive) whose iteration may run the fast body, from the input side:
+// iteration q loads the new slots of pair q+1, [2qHS + RS, 2qHS + RS + ADV), all inside [0, n)
+template <class SG>
+__device__ __forceinline__ int64_t fast_hi_input(int64_t n) {
+    const int64_t hi = n / SG::L - SG::RS - SG::ADV + 4;       // 2*q*HS <= hi
+    return hi < 0 ? -1 : hi / (2 * SG::HS);
+}
+
+// 0.5*log1p(x)/x on [0, 1/4], degree 6 (Chebyshev fit, 4.5e-8 relative in float32 Horner)
+__device__ __forceinline__ v2 half_log1p_over_x(v2 x) {
+    v2 p = vfma(x, vset(3.537580770e-02f), vset(-7.272362134e-02f));
+    p = vfma(p, x, vset(9.832768570e-02f));
+    p = vfma(p, x, vset(-1.248603150e-01f));
+    p = vfma(p, x, vset(1.666610216e-01f));
+    p = vfma(p, x, vset(-2.499999137e-01f));
+    p = vfma(p, x, vset(4.999999998e-01f));
+    return p;
+}
+// to_log gain for two bins with a2 <= 1/4: a2 * (0.5*log1p(a2)/a2) * rsqrt(a2 + eps)
+__device__ __forceinline__ v2 log_gain2_tiny(v2 a2, float eps) {
+    v2 e = vadd(a2, vset(eps));
+    v2 g = vmul(a2, half_log1p_over_x(a2));
+    return vmul(g, make_float2(rsqrtf(e.x), rsqrtf(e.y)));
 }
 
 // ---------------------------------------------------------------------------
@@ -287,17 +345,31 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((6
     const bool al = p.al_in != 0;
     int64_t base = (int64_t)2 * q0 * HS;            // padded slot of ring[0]
 
-    v2 ring[SG::RS], nxt[SG::ADV];
-    load_slots<SG::L, SG::KEEP>(row, p.n, base, j, al, ring);
-    load_slots<SG::L, SG::ADV>(row, p.n, base + SG::KEEP, j, al, nxt);
+    // fast stretch [q0, qb): loads of the next pair inside the signal, frame b exists, aligned rows
+    int qb;
+    {
+        int64_t qhi = fast_hi_input<SG>(p.n);
+        if (qhi > (p.T - 2) / 2) qhi = (p.T - 2) / 2;
+        qb = (int)(qhi + 1 < q1 ? qhi + 1 : q1);
+        if (!al || qb < q0) qb = q0;
+    }
 
-    for (int q = q0; q < q1; ++q) {
-#pragma unroll
-        for (int i = 0; i < SG::ADV; ++i) ring[SG::KEEP + i] = nxt[i];
-        if (q + 1 < q1) load_slots<SG::L, SG::ADV>(row, p.n, base + SG::RS, j, al, nxt);
+    v2 ring[SG::RS];
+    load_slots<SG::L, SG::RS>(row, p.n, base, j, al, ring);
+    const TIn* wptr = row + (base + SG::RS - 4) * SG::L + 2 * j;      // slot base + RS: first slot the next pair adds
+    float* fptr = p.feat + (b * p.T + 2 * (int64_t)q0) * N;           // feature row of frame 2q
+
+    auto step = [&](int q, auto tag) {
+        constexpr bool FAST = decltype(tag)::value;
         cv2 a[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], win[i]); a[i].im = vmul(ring[HS + i], win[i]); }
+#pragma unroll
+        for (int i = 0; i < SG::KEEP; ++i) ring[i] = ring[i + SG::ADV];
+        if (q + 1 < q1) {
+            if (FAST) load_slots_fast<SG::L, SG::ADV>(wptr, &ring[SG::KEEP]);
+            else load_slots<SG::L, SG::ADV>(row, p.n, base + SG::RS, j, al, &ring[SG::KEEP]);
+        }
         fft_forward<N>(ctx, a);
         PairSpec s;
         split_pair<N>(a, t0, s);
@@ -311,7 +383,15 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((6
                 a2b[i] = vfma(s.br[i], s.br[i], vmul(s.bi[i], s.bi[i]));
                 mx = fmaxf(fmaxf(mx, fmaxf(a2a[i].x, a2a[i].y)), fmaxf(a2b[i].x, a2b[i].y));
             }
-            if (__all_sync(0xffffffffu, mx <= 1.0f)) {
+            const bool tiny = __all_sync(0xffffffffu, mx <= 0.25f);
+            if (tiny) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v2 ga = log_gain2_tiny(a2a[i], p.eps), gb = log_gain2_tiny(a2b[i], p.eps);
+                    s.ar[i] = vmul(s.ar[i], ga); s.ai[i] = vmul(s.ai[i], ga);
+                    s.br[i] = vmul(s.br[i], gb); s.bi[i] = vmul(s.bi[i], gb);
+                }
+            } else if (__all_sync(0xffffffffu, mx <= 1.0f)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     v2 ga = log_gain2_small(a2a[i], p.eps), gb = log_gain2_small(a2b[i], p.eps);
@@ -329,27 +409,30 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((6
                 }
             }
         }
-        const int64_t ta = 2 * (int64_t)q;
-        float* ra = p.feat + (b * p.T + ta) * N;
-        const bool hb = ta + 1 < p.T;
+        float* ra = fptr + ctx.cA;
+        float* rb = fptr + ctx.cB;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
-            ra[kx] = s.ar[i].x; ra[N / 2 + kx] = s.ai[i].x;
-            ra[ky] = s.ar[i].y; ra[N / 2 + ky] = s.ai[i].y;
+            ra[SG::L * i] = s.ar[i].x; ra[N / 2 + SG::L * i] = s.ai[i].x;
+            rb[SG::L * i] = s.ar[i].y; rb[N / 2 + SG::L * i] = s.ai[i].y;
         }
-        if (hb) {
+        if (FAST || 2 * (int64_t)q + 1 < p.T) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
-                ra[N + kx] = s.br[i].x; ra[N + N / 2 + kx] = s.bi[i].x;
-                ra[N + ky] = s.br[i].y; ra[N + N / 2 + ky] = s.bi[i].y;
+                ra[N + SG::L * i] = s.br[i].x; ra[N + N / 2 + SG::L * i] = s.bi[i].x;
+                rb[N + SG::L * i] = s.br[i].y; rb[N + N / 2 + SG::L * i] = s.bi[i].y;
             }
         }
-#pragma unroll
-        for (int i = 0; i < SG::KEEP; ++i) ring[i] = ring[i + SG::ADV];
         base += SG::ADV;
-    }
+        wptr += SG::ADV * SG::L;
+        fptr += 2 * N;
+    };
+
+    int q = q0;
+#pragma unroll 1
+    for (; q < qb; ++q) step(q, FastTag());
+#pragma unroll 1
+    for (; q < q1; ++q) step(q, SlowTag());
 }
 
 // ---------------------------------------------------------------------------
@@ -473,6 +556,34 @@ struct SynthSmem {
     }
 };
 
+// mask application fused with the Hermitian pack (A7 + the input side of A8): the masked
+// spectra  Ya = ga * Xa,  Yb = gb * Xb  of the two frames go straight into the inverse
+// transform's input  Ya + i Yb  (registers 0..3: bins k; registers 4..7: bins N-k).
+template <int N>
+__device__ __forceinline__ void mask_pack_pair(const PairSpec& x, const v2 (&ga)[4], const v2 (&gb)[4], bool t0, cv2 (&a)[8]) {
+    v2 qre[4], qim[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const v2 t1 = vmul(x.bi[i], gb[i]), t2 = vmul(x.ai[i], ga[i]);
+        v2 pre = vfma(x.ar[i], ga[i], vneg(t1));      // yar - ybi
+        qre[i] = vfma(x.ar[i], ga[i], t1);            // yar + ybi
+        v2 pim = vfma(x.br[i], gb[i], t2);            // yai + ybr
+        qim[i] = vfma(x.br[i], gb[i], vneg(t2));      // ybr - yai
+        if (i == 0) {     // thread 0, lane x: (DC, Nyquist) share slot 0 and pair with themselves
+            const float yar = x.ar[0].x * ga[0].x, yai = x.ai[0].x * ga[0].x, ybr = x.br[0].x * gb[0].x, ybi = x.bi[0].x * gb[0].x;
+            pre.x = t0 ? yar : pre.x; pim.x = t0 ? ybr : pim.x;
+            qre[0].x = t0 ? yai : qre[0].x; qim[0].x = t0 ? ybi : qim[0].x;
+        }
+        a[i].re = pre; a[i].im = pim;
+    }
+#pragma unroll
+    for (int r = 4; r < 8; ++r) {
+        const int ix = (r == 4) ? 0 : 8 - r;      // thread 0, lane x: the pair whose partner lives in register r
+        a[r].re = make_float2(t0 ? qre[ix].x : qre[7 - r].y, t0 ? qre[7 - r].y : qre[7 - r].x);
+        a[r].im = make_float2(t0 ? qim[ix].x : qim[7 - r].y, t0 ? qim[7 - r].y : qim[7 - r].x);
+    }
+}
+
 template <int N, int HS, int ST, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((65536 / (WARPS * 32)) / 8) * 8) mask_istft_kernel(const SynthArgs p) {
     typedef SGeo<N, HS> SG; typedef Geo<N> G; typedef SynthSmem<N, ST> SM;
@@ -510,25 +621,47 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
     o.init(p.T, j, p.al_out != 0, (float)N);
     float* orow0 = p.out + (b * p.S + s0) * p.ld_out;
     const float* mrow0 = p.mask + ((b * p.S + s0) * p.T) * NH;       // source s: + s*T*NH; frame t: + t*NH
+    const int64_t msrc = p.T * NH;                                   // mask stride between sources
 
-    // one lane stages the masks of pair q into stage (q - qs) & 1
+    // one lane stages the masks of pair q into stage (q - qs) & 1 (shared-memory addresses kept as
+    // 32-bit values so that the elected lane only moves them to uniform registers)
+    const uint32_t stage_s = smem_u32(stage), bars_s = smem_u32(bars);
     auto prefetch = [&](int q) {
-        if (j == 0) {
-            const int st = (q - qs) & 1;
+        if (elect_one()) {
+            const uint32_t st = (uint32_t)(q - qs) & 1u;
             const int64_t ta = 2 * (int64_t)q;
             const uint32_t bytes = (ta + 1 < p.T ? 2 : 1) * NH * (uint32_t)sizeof(float);
-            mbar_expect_tx(&bars[st], bytes * ns);
-            for (int s = 0; s < ns; ++s)
-                tma_load_1d(stage + st * SM::STAGE_FLOATS + s * 2 * NH, mrow0 + ((int64_t)s * p.T + ta) * NH, bytes, &bars[st]);
+            const uint32_t bar = bars_s + st * 8u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * ns) : "memory");
+            const float* src = mrow0 + ta * NH;
+            const uint32_t dst = stage_s + st * (uint32_t)(SM::STAGE_FLOATS * sizeof(float));
+#pragma unroll
+            for (int s = 0; s < ST; ++s)
+                if (s < ns)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst + s * (uint32_t)(2 * NH * sizeof(float))), "l"(src + s * msrc), "r"(bytes), "r"(bar) : "memory");
         }
     };
 
     const float* row = p.wave + b * p.ld;
     const bool al = p.al_in != 0;
 
-    // overlap-add state carried between pairs: KEEP slots per source.  The source loop is a
-    // real loop (one copy of the inverse transform in the instruction stream); the
-    // accumulators rotate through acc[0] so that indexing stays static.
+    // fast stretch [qa, qb): own pairs whose input slots (incl. the next pair's loads) lie inside the
+    // signal, whose ADV output slots are interior (covered by R frames), with both frames present
+    int qa, qb;
+    {
+        int64_t qhi = fast_hi_input<SG>(p.n);
+        const int64_t hi_out = (p.T - 1) * HS + (HS < 4 ? HS : 4) - SG::ADV;     // base + ADV <= (T-1)HS + min(HS,4)
+        const int64_t qo = hi_out < 0 ? -1 : hi_out / (2 * HS);
+        if (qo < qhi) qhi = qo;
+        if (qhi > (p.T - 2) / 2) qhi = (p.T - 2) / 2;
+        constexpr int lo_base = (8 - HS) > 4 ? (8 - HS) : 4;                     // base >= max(8 - HS, 4)
+        qa = max(q0, (lo_base + 2 * HS - 1) / (2 * HS));
+        qb = (int)(qhi + 1 < q1 ? qhi + 1 : q1);
+        if (!al || !p.al_out || ns != ST || qb <= qa) { qa = q1; qb = q1; }
+    }
+
+    // overlap-add state carried between pairs: KEEP slots per source
     v2 acc[ST][SG::KEEP];
 #pragma unroll
     for (int s = 0; s < ST; ++s)
@@ -536,76 +669,88 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
         for (int i = 0; i < SG::KEEP; ++i) acc[s][i] = make_float2(0.f, 0.f);
 
     int64_t base = (int64_t)2 * qs * HS;
-    v2 ring[SG::RS], nxt[SG::ADV];
+    v2 ring[SG::RS];
     prefetch(qs);
-    load_slots<SG::L, SG::KEEP>(row, p.n, base, j, al, ring);
-    load_slots<SG::L, SG::ADV>(row, p.n, base + SG::KEEP, j, al, nxt);
+    load_slots<SG::L, SG::RS>(row, p.n, base, j, al, ring);
+    const float* wptr = row + (base + SG::RS - 4) * SG::L + 2 * j;      // first slot the next pair adds
+    float* optr = orow0 + (base - 4) * SG::L + 2 * j;                   // output slot `base` of source s0
+    const float* mA = stage + ctx.cA;
+    const float* mB = stage + ctx.cB;
 
 #ifdef GSS_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
-    for (int q = qs; q < q1; ++q) {
+    auto step = [&](int q, auto tag) {
+        constexpr bool FAST = decltype(tag)::value;
         GSS_T(7);
-#pragma unroll
-        for (int i = 0; i < SG::ADV; ++i) ring[SG::KEEP + i] = nxt[i];
-        if (q + 1 < q1) {
-            // the other stage was last read in iteration q-1; every lane has passed a __syncwarp since
-            prefetch(q + 1);
-            load_slots<SG::L, SG::ADV>(row, p.n, base + SG::RS, j, al, nxt);
-        }
         PairSpec x;
         {
             cv2 a[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], win[i]); a[i].im = vmul(ring[HS + i], win[i]); }
+#pragma unroll
+            for (int i = 0; i < SG::KEEP; ++i) ring[i] = ring[i + SG::ADV];
+            if (q + 1 < q1) {
+                // the other stage was last read in iteration q-1; every lane has passed a __syncwarp since
+                prefetch(q + 1);
+                if (FAST) load_slots_fast<SG::L, SG::ADV>(wptr, &ring[SG::KEEP]);
+                else load_slots<SG::L, SG::ADV>(row, p.n, base + SG::RS, j, al, &ring[SG::KEEP]);
+            }
             fft_forward<N>(ctx, a);
             split_pair<N>(a, t0, x);
         }
         GSS_T(0);
-        const int64_t ta = 2 * (int64_t)q;
-        const bool hb = ta + 1 < p.T;
+        const bool hb = FAST || 2 * (int64_t)q + 1 < p.T;
         const int stg = (q - qs) & 1;
         mbar_wait(&bars[stg], ((q - qs) >> 1) & 1);
         GSS_T(1);
-        const float* mst = stage + stg * SM::STAGE_FLOATS;
-        const bool own = q >= q0;
-        const bool fast = own && o.interior(base);
-#pragma unroll 1
-        for (int s = 0; s < ST; ++s) {
-            if (s < ns) {
-                const float* ma = mst + s * 2 * NH;
-                v2 yar[4], yai[4], ybr[4], ybi[4];
+        const float* ma = mA + stg * SM::STAGE_FLOATS;
+        const float* mb = mB + stg * SM::STAGE_FLOATS;
+        const bool own = FAST || q >= q0;
+        // one source: masks -> inverse transform -> overlap-add -> finished slots to global memory.
+        // `as` = accumulator set (static), `s` = source index (static when the loop is unrolled)
+        auto source = [&](auto as_c, int s) {
+            constexpr int as = decltype(as_c)::value;
+            v2 ga[4], gb[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
-                    v2 ga = make_float2(ma[kx], ma[ky]);
-                    v2 gb = hb ? make_float2(ma[NH + kx], ma[NH + ky]) : make_float2(0.f, 0.f);
-                    yar[i] = vmul(x.ar[i], ga); yai[i] = vmul(x.ai[i], ga);
-                    ybr[i] = vmul(x.br[i], gb); ybi[i] = vmul(x.bi[i], gb);
-                }
-                cv2 a[8];
-                pack_pair<N>(yar, yai, ybr, ybi, t0, a);
-                GSS_T(2);
-                fft_inverse<N>(ctx, a);
-                GSS_T(3);
-                v2 cur[SG::RS];
-#pragma unroll
-                for (int i = 0; i < SG::RS; ++i) cur[i] = i < SG::KEEP ? acc[0][i] : make_float2(0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    cur[i] = vfma(a[i].re, win[i], cur[i]);
-                    cur[HS + i] = vfma(a[i].im, win[i], cur[HS + i]);
-                }
-                if (own) {
-                    float* orow = orow0 + s * p.ld_out;
-#pragma unroll
-                    for (int i = 0; i < SG::ADV; ++i) o.write(orow, base + i, i % HS, cur[i], fast);
-                }
-#pragma unroll
-                for (int i = 0; i < SG::KEEP; ++i) acc[0][i] = cur[i + SG::ADV];
-                GSS_T(4);
+            for (int i = 0; i < 4; ++i) {
+                ga[i] = make_float2(ma[s * 2 * NH + SG::L * i], mb[s * 2 * NH + SG::L * i]);
+                gb[i] = hb ? make_float2(ma[s * 2 * NH + NH + SG::L * i], mb[s * 2 * NH + NH + SG::L * i]) : make_float2(0.f, 0.f);
             }
-            if (ST > 1) {            // rotate: acc[0] <- acc[1] <- ... <- acc[ST-1] <- acc[0]
+            cv2 a[8];
+            mask_pack_pair<N>(x, ga, gb, t0, a);
+            GSS_T(2);
+            fft_inverse<N>(ctx, a);
+            GSS_T(3);
+            v2 cur[SG::RS];
+#pragma unroll
+            for (int i = 0; i < SG::RS; ++i) cur[i] = i < SG::KEEP ? acc[as][i] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cur[i] = vfma(a[i].re, win[i], cur[i]);
+                cur[HS + i] = vfma(a[i].im, win[i], cur[HS + i]);
+            }
+            if (FAST) {
+                float* os = optr + s * p.ld_out;
+#pragma unroll
+                for (int i = 0; i < SG::ADV; ++i)
+                    *reinterpret_cast<float2*>(os + i * SG::L) = vmul(cur[i], SG::CONST_NORM ? vset(o.oscale) : o.invn[i % HS]);
+            } else if (own) {
+                float* orow = orow0 + s * p.ld_out;
+#pragma unroll
+                for (int i = 0; i < SG::ADV; ++i) o.write(orow, base + i, i % HS, cur[i], false);
+            }
+#pragma unroll
+            for (int i = 0; i < SG::KEEP; ++i) acc[as][i] = cur[i + SG::ADV];
+            GSS_T(4);
+        };
+        if (GSS_ROLL_SOURCES && ST > 1) {
+            // rolled: one copy of the inverse transform in the instruction stream (the loop body of
+            // three unrolled sources outgrows the 32 KB instruction cache); the accumulator sets
+            // rotate through set 0 so that register indexing stays static
+#pragma unroll 1
+            for (int s = 0; s < ST; ++s) {
+                if (FAST || s < ns) source(std::integral_constant<int, 0>(), s);
 #pragma unroll
                 for (int i = 0; i < SG::KEEP; ++i) {
                     v2 t = acc[0][i];
@@ -614,10 +759,27 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
                     acc[ST - 1][i] = t;
                 }
             }
+        } else {
+            if (FAST || 0 < ns) source(std::integral_constant<int, 0>(), 0);
+            if (ST > 1 && (FAST || 1 < ns)) source(std::integral_constant<int, (ST > 1 ? 1 : 0)>(), 1);
+            if (ST > 2 && (FAST || 2 < ns)) source(std::integral_constant<int, (ST > 2 ? 2 : 0)>(), 2);
+            if (ST > 3 && (FAST || 3 < ns)) source(std::integral_constant<int, (ST > 3 ? 3 : 0)>(), 3);
         }
-#pragma unroll
-        for (int i = 0; i < SG::KEEP; ++i) ring[i] = ring[i + SG::ADV];
         base += SG::ADV;
+        wptr += SG::ADV * SG::L;
+        optr += SG::ADV * SG::L;
+    };
+
+    int q = qs;
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+        const int qe = ph == 0 ? qa : q1;
+#pragma unroll 1
+        for (; q < qe; ++q) step(q, SlowTag());
+        if (ph == 0) {
+#pragma unroll 1
+            for (; q < qb; ++q) step(q, FastTag());
+        }
     }
     if (c == p.nchunk - 1) {
 #pragma unroll

@@ -130,6 +130,20 @@ int gss_mask_istft_d2h(const float* wave_d, const float* mask_d, int64_t B, int 
                        int64_t ld, int N, int H, float* out_d, float* out_h, int64_t ld_out,
                        int chunks, void* stream);
 
+/* Non-blocking forms for a batch loop (main.py:749-771 run over many clips): they only enqueue -
+ * uploads on the library's H2D stream, kernels on `stream`, downloads on the library's D2H
+ * stream - so the upload of batch k+1 and the download of batch k share the link in both
+ * directions.  Ordering the library guarantees: the upload starts after everything already
+ * enqueued on `stream` (wave_d may be reused); the synthesis kernels start after a pending
+ * download from the same out_d.  The caller double-buffers wave_d/feat_d/out_d/out_h and calls
+ * gss_wait_host(out_h) before reading out_h (NULL: wait for every pending download). */
+int gss_stft_h2d_async(const float* wave_h, float* wave_d, int64_t B, int64_t n, int64_t ld, int N,
+                       int H, int flags, float eps, float* feat_d, int chunks, void* stream);
+int gss_mask_istft_d2h_async(const float* wave_d, const float* mask_d, int64_t B, int S, int64_t n,
+                             int64_t ld, int N, int H, float* out_d, float* out_h,
+                             int64_t ld_out, int chunks, void* stream);
+int gss_wait_host(const void* host_ptr);
+
 #ifdef __cplusplus
 }
 #endif

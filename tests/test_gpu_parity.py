@@ -337,3 +337,54 @@ def test_ae_loss_and_wav16(T, ops, golden):
     ref = np.stack([R.wav16_normalise(r) for r in x])
     assert np.max(np.abs(pcm.astype(np.int32) - ref.astype(np.int32))) <= 1   # +-1 LSB
     assert pcm.min() == 0 and pcm.max() >= 32766
+
+
+# --------------------------------------------------------------------------
+# host-buffer pipeline (gss_stft_h2d / gss_mask_istft_d2h and their non-blocking forms)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("depth", [1, 2])
+def test_spectral_pipeline_matches_oracle(T, ops, depth):
+    from gan_sass_tf_b200.app.spectral import SpectralPipeline
+    N, H, n, B, S = 512, 128, 6000, 6, 3
+    rng = np.random.default_rng(5 + depth)
+    pipe = SpectralPipeline(B, n, S, N, H, chunks=3, depth=depth)
+    Tn = pipe.T
+    batches = [speechish(rng, B, n) for _ in range(5)]
+    masks = [rng.random((B, S, Tn, N // 2)).astype(np.float32) for _ in range(5)]
+    got = [None] * 5
+    feats = [None] * 5
+    for k in range(5):
+        slot = k % depth
+        if k >= depth:
+            got[k - depth] = pipe.wait(slot).numpy().copy()
+        f = pipe.analyse(batches[k], slot=slot, block=(depth == 1))
+        feats[k] = f.clone()                                   # ordered on the current stream
+        pipe.synthesise(dev(T, masks[k]), slot=slot, block=(depth == 1))
+        if depth == 1:
+            got[k] = pipe.out_h.numpy().copy()
+    for k in range(max(0, 5 - depth), 5):
+        if got[k] is None:
+            got[k] = pipe.wait(k % depth).numpy().copy()
+    for k in range(5):
+        ref = R.mask_istft_np(batches[k], masks[k], N, H).reshape(B * S, -1)
+        assert got[k].shape == ref.shape
+        assert R.rel_l2(got[k], ref) < REL_L2, f"batch {k}"
+        assert R.rel_l2(feats[k].cpu().numpy(), R.to_log_signal(R.stft_feature_np(batches[k], N, H))) < REL_L2, f"features {k}"
+
+
+@pytest.mark.parametrize("n", [1024, 1025, 2047, 4096, 4100])
+@pytest.mark.parametrize("H", [64, 128, 256])
+def test_short_and_ragged_lengths_cover_both_loop_bodies(T, ops, n, H):
+    """the streaming kernels walk slow (edges) - fast (interior) - slow stretches; lengths around
+    the boundaries of the fast stretch, with aligned (even n) and unaligned (odd n) rows."""
+    N, B, S = 512, 3, 3
+    rng = np.random.default_rng(n + H)
+    x = speechish(rng, B, n)
+    Tn, _ = R.frame_count(n, N, H)
+    mask = rng.random((B, S, Tn, N // 2)).astype(np.float32)
+    ref_f = R.stft_feature_np(x, N, H)
+    ref_y = R.mask_istft_np(x, mask, N, H).reshape(B * S, -1)
+    xd = dev(T, x)                                # odd n: every second row is unaligned (slow body only)
+    assert R.rel_l2(ops.stft(xd, N, H).cpu().numpy(), ref_f) < REL_L2
+    assert R.rel_l2(ops.stft_log(xd, N, H).cpu().numpy(), R.to_log_signal(ref_f)) < REL_L2
+    assert R.rel_l2(ops.mask_istft(xd, dev(T, mask), N, H).cpu().numpy(), ref_y) < REL_L2

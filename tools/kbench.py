@@ -38,6 +38,12 @@ for S in (1, 2, 3, 4):
     timeit(f"mask_istft S={S}", lambda i: ops.mask_istft(waves[i % 3], masks[i % 3], N, H, out=out),
            4 * B * (n + S * T * N // 2 + S * (T - 1) * H))
     del masks
+if "--torch" in sys.argv:   # courtesy baseline: cuFFT through torch.stft / torch.istft on the same GPU
+    w_ = torch.hann_window(N, periodic=True, device=dev)
+    spec = [torch.stft(w, N, H, window=w_, center=True, pad_mode="constant", return_complex=True) for w in waves]
+    timeit("torch.stft (cuFFT)", lambda i: torch.stft(waves[i % 3], N, H, window=w_, center=True, pad_mode="constant", return_complex=True), 4 * B * (n + T * N))
+    timeit("torch.istft (cuFFT)", lambda i: torch.istft(spec[i % 3], N, H, window=w_, center=True, length=n), 4 * B * (T * N + (T - 1) * H))
+    del spec
 x = feat[0]
 from gan_sass_tf_b200.app import hparams
 hparams.FFT_SIZE = N
