@@ -99,10 +99,39 @@ def istft(feature, hop=None, length=None, exp=False):
     return out if length is None else out[..., :length]
 
 
+class _ApplyMask(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mix_feature, mask):
+        x, m = _f32c(mix_feature, "apply_mask"), _f32c(mask, "apply_mask")
+        ctx.save_for_backward(x, m)
+        return _apply_mask_fwd(x, m)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, m = ctx.saved_tensors
+        g = _f32c(gout, "apply_mask")
+        B, T, N = x.shape
+        S = m.shape[1]
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gm = torch.empty_like(m) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(x.device):
+            _n.check(_n.lib().gss_apply_mask_bwd(x.data_ptr(), m.data_ptr(), g.data_ptr(), B, S, T, N,
+                                                 gx.data_ptr() if gx is not None else None,
+                                                 gm.data_ptr() if gm is not None else None, _stream()))
+        return gx, gm
+
+
 def apply_mask(mix_feature, mask):
     """``mix_feature [B,T,N]``, ``mask [B,S,T,N/2]`` -> ``[B*S,T,N]``: one real gain per
     complex bin (both packed halves; slot 0 = DC+Nyquist share a gain, the pairing
-    of ops.py:234-237), output row ``b*S+s`` (modules.py:396-399)."""
+    of ops.py:234-237), output row ``b*S+s`` (modules.py:396-399).  Differentiable in both
+    arguments (``gss_apply_mask_bwd``)."""
+    if torch.is_grad_enabled() and (getattr(mix_feature, "requires_grad", False) or getattr(mask, "requires_grad", False)):
+        return _ApplyMask.apply(mix_feature, mask)
+    return _apply_mask_fwd(mix_feature, mask)
+
+
+def _apply_mask_fwd(mix_feature, mask):
     x = _f32c(mix_feature, "apply_mask")
     m = _f32c(mask, "apply_mask")
     assert x.dim() == 3 and m.dim() == 4, "apply_mask: mix [B,T,N], mask [B,S,T,N/2]"
@@ -150,13 +179,56 @@ def _logexp(s_signal, fn_name):
     return out
 
 
+def _logexp_bwd(x, gout, fn_name):
+    N = hparams.FFT_SIZE
+    g = _f32c(gout, fn_name)
+    gin = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _n.check(getattr(_n.lib(), fn_name)(x.data_ptr(), g.data_ptr(), gin.data_ptr(), x.numel() // N, N, hparams.EPS, _stream()))
+    return gin
+
+
+class _ToLog(torch.autograd.Function):
+    """to_log_signal with the hand-written backward kernel (the reference back-propagates through
+    it: main.py:338 sits under the optimisers of main.py:481-484)."""
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x, "to_log_signal")
+        ctx.save_for_backward(x)
+        return _logexp(x, "gss_to_log")
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        return _logexp_bwd(x, gout, "gss_to_log_bwd")
+
+
+class _ToExp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x, "to_exp_signal")
+        ctx.save_for_backward(x)
+        return _logexp(x, "gss_to_exp")
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        return _logexp_bwd(x, gout, "gss_to_exp_bwd")
+
+
 def to_log_signal(s_signal):
-    """ops.py:228-238: each bin pair ``(k, k+N/2)`` scaled by ``0.5*log1p(a2)*rsqrt(a2+EPS)``."""
+    """ops.py:228-238: each bin pair ``(k, k+N/2)`` scaled by ``0.5*log1p(a2)*rsqrt(a2+EPS)``.
+    Differentiable (``gss_to_log_bwd``)."""
+    if torch.is_grad_enabled() and isinstance(s_signal, torch.Tensor) and s_signal.requires_grad:
+        return _ToLog.apply(s_signal)
     return _logexp(s_signal, "gss_to_log")
 
 
 def to_exp_signal(s_signal):
-    """ops.py:241-251: ``a = sqrt(re^2+im^2+EPS)``, scale ``expm1(a)/a`` (not the inverse of to_log, K7)."""
+    """ops.py:241-251: ``a = sqrt(re^2+im^2+EPS)``, scale ``expm1(a)/a`` (not the inverse of to_log, K7).
+    Differentiable (``gss_to_exp_bwd``)."""
+    if torch.is_grad_enabled() and isinstance(s_signal, torch.Tensor) and s_signal.requires_grad:
+        return _ToExp.apply(s_signal)
     return _logexp(s_signal, "gss_to_exp")
 
 
@@ -213,3 +285,72 @@ def wav16_normalise(wave):
     with torch.cuda.device(x.device):
         _n.check(_n.lib().gss_wav16_normalise(x2.data_ptr(), R, n, n, mm.data_ptr(), pcm.data_ptr(), _stream()))
     return pcm.reshape(x.shape)
+
+
+# ---------------------------------------------------------------------------
+# feature-domain mixing (main.py:328-338)
+# ---------------------------------------------------------------------------
+def mix_signals(s_src_signals, n_signal=None, noise=None, noise_stddev=0.1, generator=None, log=False):
+    """main.py:328-337: ``src [B*n_sig, T, N]`` packed features -> mixture ``[B, T, N]`` =
+    ``sum_i src[b*n_sig+i] + noise``.  ``noise``: a tensor ``[B,T,N]``, ``None`` to draw
+    ``N(0, noise_stddev^2)`` on the device (the reference's ``tf.random_normal(stddev=0.1)``;
+    ``generator`` makes the draw reproducible), or ``False`` for no noise.  ``log=True`` returns
+    ``(mix, to_log_signal(mix))`` from one fused pass (main.py:338)."""
+    x = _f32c(s_src_signals, "mix_signals")
+    n_sig = hparams.MAX_N_SIGNAL if n_signal is None else int(n_signal)
+    assert x.dim() == 3 and x.shape[0] % n_sig == 0, "mix_signals: src must be [B*n_sig, T, N]"
+    B, T, N = x.shape[0] // n_sig, x.shape[1], x.shape[2]
+    if noise is None:
+        noise = torch.randn((B, T, N), dtype=torch.float32, device=x.device, generator=generator) * noise_stddev
+    elif noise is False:
+        noise = None
+    else:
+        noise = _f32c(noise, "mix_signals")
+        assert noise.shape == (B, T, N), f"mix_signals: noise shape {tuple(noise.shape)} != {(B, T, N)}"
+    mix = torch.empty((B, T, N), dtype=torch.float32, device=x.device)
+    mix_log = torch.empty_like(mix) if log else None
+    with torch.cuda.device(x.device):
+        _n.check(_n.lib().gss_mix_features(x.data_ptr(), noise.data_ptr() if noise is not None else None, B, n_sig, T, N,
+                                           _n.FLAG_LOG if log else 0, hparams.EPS, mix.data_ptr(),
+                                           mix_log.data_ptr() if log else None, _stream()))
+    return (mix, mix_log) if log else mix
+
+
+def snr_metric(s_src_signals, s_separated_signals, n_signal=None):
+    """main.py:446-457: cross SNR of every (source, output) pair, max over outputs, mean over
+    batch and sources.  ``src [B*n_sig,T,N]``, ``sep [B*S,T,N]`` -> scalar tensor."""
+    n_sig = hparams.MAX_N_SIGNAL if n_signal is None else int(n_signal)
+    B = s_src_signals.shape[0] // n_sig
+    T, N = s_src_signals.shape[-2:]
+    cs = batch_cross_snr(s_src_signals.reshape(B, n_sig, T, N), s_separated_signals.reshape(B, -1, T, N))
+    return cs.max(dim=-1).values.mean()
+
+
+# ---------------------------------------------------------------------------
+# demo-mode edges (main.py:83-95)
+# ---------------------------------------------------------------------------
+def resample_pad_size(length, fft_size=None):
+    """main.py:93: zero-padding after the resample branch, ``N - ((L-1) mod N) - 1``."""
+    N = hparams.FFT_SIZE if fft_size is None else int(fft_size)
+    return N - ((int(length) - 1) % N) - 1
+
+
+def resample(wave, num):
+    """``scipy.signal.resample(x, num)`` (Fourier method, main.py:92) along the last axis of a
+    real CUDA tensor.  One long rFFT / irFFT pair: this edge op calls cuFFT through ``torch.fft``
+    (a library call, not one of the hand-written kernels; SURVEY 8f.3 lists it as "next")."""
+    x = _dev(wave, "resample").to(torch.float64 if wave.dtype == torch.float64 else torch.float32)
+    n, num = x.shape[-1], int(num)
+    assert n >= 1 and num >= 1
+    X = torch.fft.rfft(x, dim=-1)
+    m = min(n, num)
+    nyq = m // 2 + 1
+    Y = torch.zeros(x.shape[:-1] + (num // 2 + 1,), dtype=X.dtype, device=x.device)
+    Y[..., :nyq] = X[..., :nyq]
+    if m % 2 == 0:                       # the shared Nyquist bin (scipy.signal.resample, real input)
+        if num < n:
+            Y[..., m // 2] = Y[..., m // 2] * 2.0      # down-sampling: fold the two halves of the bin
+        elif num > n:
+            Y[..., m // 2] = Y[..., m // 2] * 0.5      # up-sampling: split it
+    y = torch.fft.irfft(Y, n=num, dim=-1)
+    return y * (float(num) / float(n))

@@ -257,6 +257,7 @@ template <int N, int HS>
 int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
     // sources carried per pass: 3 when S is a multiple of 3, else 2 (S even) or 1
     if (a.S % 3 == 0) return launch_synth<N, HS, 3>(a, st);
+    if (a.S % 4 == 0 && HS == 2) return launch_synth<N, HS, 4>(a, st);
     if (a.S % 2 == 0) return launch_synth<N, HS, 2>(a, st);
     if (a.S == 1) return launch_synth<N, HS, 1>(a, st);
     return launch_synth<N, HS, 3>(a, st);
@@ -430,6 +431,48 @@ static int logexp(bool ex, const float* in, float* out, int64_t rows, int N, flo
 }
 int gss_to_log(const float* in, float* out, int64_t rows, int N, float eps, void* stream) { return logexp(false, in, out, rows, N, eps, stream); }
 int gss_to_exp(const float* in, float* out, int64_t rows, int N, float eps, void* stream) { return logexp(true, in, out, rows, N, eps, stream); }
+
+int gss_mix_features(const float* src, const float* noise, int64_t B, int n_sig, int64_t T, int N, int flags, float eps,
+                     float* mix, float* mix_log, void* stream) {
+    if (!src) return fail(GSS_EINVAL, "mix_features: null pointer");
+    if (N < 8 || N % 8) return fail(GSS_EINVAL, "mix_features: N=%d must be a multiple of 8", N);
+    if (B < 0 || n_sig < 1 || T < 0) return fail(GSS_EINVAL, "mix_features: bad shape");
+    if (flags & ~GSS_FLAG_LOG) return fail(GSS_EINVAL, "mix_features: unknown flags 0x%x", flags);
+    const bool lg = flags & GSS_FLAG_LOG;
+    if (lg ? !mix_log : !mix) return fail(GSS_EINVAL, "mix_features: output pointer missing");
+    if (((uintptr_t)src | (uintptr_t)noise | (uintptr_t)mix | (uintptr_t)mix_log) & 15) return fail(GSS_EINVAL, "mix_features: buffers must be 16-byte aligned");
+    const int64_t total = B * T * (N / 8);
+    if (total == 0) return GSS_OK;
+    if (lg) gss::mix_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, noise, mix, mix_log, B, n_sig, T, N, eps);
+    else gss::mix_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, noise, mix, nullptr, B, n_sig, T, N, eps);
+    return after_launch("mix_kernel");
+}
+
+static int logexp_bwd(bool ex, const float* in, const float* gout, float* gin, int64_t rows, int N, float eps, void* stream) {
+    if (!in || !gout || !gin) return fail(GSS_EINVAL, "to_log/to_exp backward: null pointer");
+    if (N < 8 || N % 8) return fail(GSS_EINVAL, "to_log/to_exp backward: N=%d must be a multiple of 8", N);
+    if (rows < 0) return fail(GSS_EINVAL, "to_log/to_exp backward: rows < 0");
+    if (((uintptr_t)in | (uintptr_t)gout | (uintptr_t)gin) & 15) return fail(GSS_EINVAL, "to_log/to_exp backward: buffers must be 16-byte aligned");
+    const int64_t total = rows * (N / 8);
+    if (total == 0) return GSS_OK;
+    if (ex) gss::logexp_bwd_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, gout, gin, rows, N, eps);
+    else gss::logexp_bwd_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, gout, gin, rows, N, eps);
+    return after_launch("logexp_bwd_kernel");
+}
+int gss_to_log_bwd(const float* in, const float* gout, float* gin, int64_t rows, int N, float eps, void* stream) { return logexp_bwd(false, in, gout, gin, rows, N, eps, stream); }
+int gss_to_exp_bwd(const float* in, const float* gout, float* gin, int64_t rows, int N, float eps, void* stream) { return logexp_bwd(true, in, gout, gin, rows, N, eps, stream); }
+
+int gss_apply_mask_bwd(const float* mix, const float* mask, const float* gout, int64_t B, int S, int64_t T, int N,
+                       float* gmix, float* gmask, void* stream) {
+    if (!mix || !mask || !gout || (!gmix && !gmask)) return fail(GSS_EINVAL, "apply_mask_bwd: null pointer");
+    if (N < 8 || N % 8) return fail(GSS_EINVAL, "apply_mask_bwd: N=%d must be a multiple of 8", N);
+    if (B < 0 || S < 1 || T < 0) return fail(GSS_EINVAL, "apply_mask_bwd: bad shape");
+    if (((uintptr_t)mix | (uintptr_t)mask | (uintptr_t)gout | (uintptr_t)gmix | (uintptr_t)gmask) & 15) return fail(GSS_EINVAL, "apply_mask_bwd: buffers must be 16-byte aligned");
+    const int64_t total = B * T * (N / 8);
+    if (total == 0) return GSS_OK;
+    gss::apply_mask_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mix, mask, gout, gmix, gmask, B, S, T, N);
+    return after_launch("apply_mask_bwd_kernel");
+}
 
 int gss_cross_snr(const float* clear, const float* noisy, int64_t B, int m, int n, int64_t L, float eps, float* snr, void* stream) {
     if (!clear || !noisy || !snr) return fail(GSS_EINVAL, "cross_snr: null pointer");

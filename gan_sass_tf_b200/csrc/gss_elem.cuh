@@ -138,4 +138,114 @@ __global__ void __launch_bounds__(256) wav16_kernel(const float* __restrict__ x,
     }
 }
 
+// ---------------------------------------------------------------------------
+// A10 (main.py:328-337): mix[b] = sum_i src[b,i] (+ noise[b]) on packed features, optionally
+// followed by to_log_signal (main.py:338) in the same pass.  rows = B*T, a thread handles bins
+// k..k+3 of both halves of a row (the to_log gain couples bin k with bin k + N/2).
+// ---------------------------------------------------------------------------
+template <bool LOG>
+__global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ src, const float* __restrict__ noise,
+                                                  float* __restrict__ mix, float* __restrict__ mix_log,
+                                                  int64_t B, int n_sig, int64_t T, int N, float eps) {
+    const int q = N / 8;
+    const int64_t total = B * T * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / q; const int k4 = (int)(i - r * q);       // r = b*T + t
+        const int64_t b = r / T, t = r - b * T;
+        float4 re = make_float4(0.f, 0.f, 0.f, 0.f), im = re;
+        for (int s = 0; s < n_sig; ++s) {
+            const float4* ps = reinterpret_cast<const float4*>(src + ((b * n_sig + s) * T + t) * N) + k4;
+            const float4 a = __ldg(ps), c = __ldg(ps + q);
+            re.x += a.x; re.y += a.y; re.z += a.z; re.w += a.w;
+            im.x += c.x; im.y += c.y; im.z += c.z; im.w += c.w;
+        }
+        if (noise) {
+            const float4* pn = reinterpret_cast<const float4*>(noise + r * N) + k4;
+            const float4 a = __ldg(pn), c = __ldg(pn + q);
+            re.x += a.x; re.y += a.y; re.z += a.z; re.w += a.w;
+            im.x += c.x; im.y += c.y; im.z += c.z; im.w += c.w;
+        }
+        if (mix) { float4* po = reinterpret_cast<float4*>(mix + r * N) + k4; po[0] = re; po[q] = im; }
+        if (LOG) {
+            float g;
+#define GSS_G(c) g = log_gain(re.c, im.c, eps); re.c *= g; im.c *= g;
+            GSS_G(x) GSS_G(y) GSS_G(z) GSS_G(w)
+#undef GSS_G
+            float4* po = reinterpret_cast<float4*>(mix_log + r * N) + k4; po[0] = re; po[q] = im;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Backward passes of the element-wise ops the reference back-propagates through
+// (to_log_signal / to_exp_signal, app/ops.py:228-251; optimisers main.py:481-484) and of the
+// mask multiply.  y = g(a2) * (re, im), a2 = re^2 + im^2:
+//   d(re) = g*d(y_re) + 2 g'(a2) re (re d(y_re) + im d(y_im)),   same for im.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void log_gain_d(float a2, float eps, float& g, float& dg) {
+    const float l = 0.5f * log1pf(a2), e = a2 + eps, rs = rsqrtf(e);
+    g = l * rs;
+    dg = 0.5f * rs / (1.0f + a2) - 0.5f * l * rs / e;          // d/da2 [0.5 log1p(a2) (a2+eps)^-1/2]
+}
+__device__ __forceinline__ void exp_gain_d(float a2, float eps, float& g, float& dg) {
+    const float a = sqrtf(a2 + eps), em = expm1f(a);
+    g = em / a;
+    // d/da [expm1(a)/a] = (a e^a - expm1(a)) / a^2 ;  da/da2 = 1/(2a).  Small a: series (1/2 + a/3 + a^2/8 + a^3/30)
+    const float dga = a < 0.05f ? fmaf(a, fmaf(a, fmaf(a, 1.0f / 30.0f, 0.125f), 1.0f / 3.0f), 0.5f)
+                                : (a * (em + 1.0f) - em) / (a * a);
+    dg = dga / (2.0f * a);
+}
+
+template <bool EXP>
+__global__ void __launch_bounds__(256) logexp_bwd_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                         float* __restrict__ gin, int64_t rows, int N, float eps) {
+    const int q = N / 8;
+    const int64_t total = rows * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / q; const int k4 = (int)(i - r * q);
+        const float4* pr = reinterpret_cast<const float4*>(in + r * N) + k4;
+        const float4* pg = reinterpret_cast<const float4*>(gout + r * N) + k4;
+        const float4 re = __ldg(pr), im = __ldg(pr + q), gr = __ldg(pg), gi = __ldg(pg + q);
+        float4 dr, di;
+#define GSS_B(c) { float g, dg; const float a2 = fmaf(re.c, re.c, im.c * im.c); \
+                   if (EXP) exp_gain_d(a2, eps, g, dg); else log_gain_d(a2, eps, g, dg); \
+                   const float dot = 2.0f * dg * fmaf(re.c, gr.c, im.c * gi.c); \
+                   dr.c = fmaf(g, gr.c, dot * re.c); di.c = fmaf(g, gi.c, dot * im.c); }
+        GSS_B(x) GSS_B(y) GSS_B(z) GSS_B(w)
+#undef GSS_B
+        float4* po = reinterpret_cast<float4*>(gin + r * N) + k4;
+        po[0] = dr; po[q] = di;
+    }
+}
+
+// out[b,s,t] = mask[b,s,t] (x) mix[b,t]:  gmix[b,t] = sum_s mask * gout,  gmask[b,s,t,k] = re*gout_re + im*gout_im
+__global__ void __launch_bounds__(256) apply_mask_bwd_kernel(const float* __restrict__ mix, const float* __restrict__ mask,
+                                                             const float* __restrict__ gout, float* __restrict__ gmix,
+                                                             float* __restrict__ gmask, int64_t B, int S, int64_t T, int N) {
+    const int q = N / 8;
+    const int64_t total = B * T * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / q; const int k4 = (int)(i - r * q);       // r = b*T + t
+        const int64_t b = r / T, t = r - b * T;
+        const float4* pm = reinterpret_cast<const float4*>(mix + r * N) + k4;
+        const float4 re = __ldg(pm), im = __ldg(pm + q);
+        float4 ar = make_float4(0.f, 0.f, 0.f, 0.f), ai = ar;
+        for (int s = 0; s < S; ++s) {
+            const int64_t ro = (b * S + s) * T + t;
+            const float4* pg = reinterpret_cast<const float4*>(gout + ro * N) + k4;
+            const float4 gr = __ldg(pg), gi = __ldg(pg + q);
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask + ro * (N / 2)) + k4);
+            ar.x = fmaf(m.x, gr.x, ar.x); ar.y = fmaf(m.y, gr.y, ar.y); ar.z = fmaf(m.z, gr.z, ar.z); ar.w = fmaf(m.w, gr.w, ar.w);
+            ai.x = fmaf(m.x, gi.x, ai.x); ai.y = fmaf(m.y, gi.y, ai.y); ai.z = fmaf(m.z, gi.z, ai.z); ai.w = fmaf(m.w, gi.w, ai.w);
+            if (gmask) {
+                float4 d;
+                d.x = fmaf(re.x, gr.x, im.x * gi.x); d.y = fmaf(re.y, gr.y, im.y * gi.y);
+                d.z = fmaf(re.z, gr.z, im.z * gi.z); d.w = fmaf(re.w, gr.w, im.w * gi.w);
+                reinterpret_cast<float4*>(gmask + ro * (N / 2))[k4] = d;
+            }
+        }
+        if (gmix) { float4* po = reinterpret_cast<float4*>(gmix + r * N) + k4; po[0] = ar; po[q] = ai; }
+    }
+}
+
 }  // namespace gss

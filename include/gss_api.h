@@ -99,6 +99,22 @@ int gss_to_exp(const float* in, float* out, int64_t rows, int N, float eps, void
 int gss_cross_snr(const float* clear, const float* noisy, int64_t B, int m, int n, int64_t L,
                   float eps, float* snr, void* stream);
 
+/* A10 (+A3): main.py:328-338.  src [B*n_sig, T, N] packed features -> mix [B, T, N] =
+ * sum_i src[b*n_sig+i] (+ noise [B,T,N], NULL = none; the reference draws it from
+ * tf.random_normal(stddev=0.1), the caller passes the draw so that runs are reproducible).
+ * flags = GSS_FLAG_LOG additionally writes to_log_signal(mix) to mix_log in the same pass
+ * (then mix may be NULL). */
+int gss_mix_features(const float* src, const float* noise, int64_t B, int n_sig, int64_t T, int N,
+                     int flags, float eps, float* mix, float* mix_log, void* stream);
+
+/* Backward passes: the reference back-propagates through to_log_signal /
+ * to_exp_signal (app/ops.py:228-251 under the optimisers of main.py:481-484); apply_mask is the
+ * new op A7.  in / gout / gin [rows, N]; gmix [B,T,N] and gmask [B,S,T,N/2] may each be NULL. */
+int gss_to_log_bwd(const float* in, const float* gout, float* gin, int64_t rows, int N, float eps, void* stream);
+int gss_to_exp_bwd(const float* in, const float* gout, float* gin, int64_t rows, int N, float eps, void* stream);
+int gss_apply_mask_bwd(const float* mix, const float* mask, const float* gout, int64_t B, int S,
+                       int64_t T, int N, float* gmix, float* gmask, void* stream);
+
 /* A12: main.py:353-361.  sep [B,S,L], mix [B,L] -> partial[B] = sum_l (sum_s sep - mix)^2
  * (the caller divides by B*L; per-utterance partials are what the ranks all-reduce). */
 int gss_ae_partial(const float* sep, const float* mix, int64_t B, int S, int64_t L,

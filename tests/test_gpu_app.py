@@ -1,0 +1,235 @@
+"""GPU parity of the rows either side of the transforms: feature-domain mixing (A10), the
+backward kernels, demo-mode edges (A13/A14: resample, pad, WAV in/out), the toy
+config C1 end to end and the device-resident waveform dataset (8f.2).  All through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_oracle as R
+
+pytestmark = pytest.mark.gpu
+REL_L2 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gan_sass_tf_b200.app import ops as o
+    from gan_sass_tf_b200 import _native
+    _native.lib()
+    return o
+
+
+@pytest.fixture()
+def hp():
+    from gan_sass_tf_b200.app import hparams
+    saved = {k: getattr(hparams, k) for k in ("FFT_SIZE", "HOP_SIZE", "SEPARATOR_TYPE", "DATASET_TYPE", "BATCH_SIZE", "MAX_N_SIGNAL")}
+    yield hparams
+    for k, v in saved.items():
+        setattr(hparams, k, v)
+
+
+def dev(T, a):
+    return T.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- A10 --------------------------------------------------------------------------
+@pytest.mark.parametrize("B,n_sig,Tn,N", [(8, 3, 128, 256), (2, 2, 37, 512), (1, 4, 5, 64)])
+def test_mix_signals_matches_oracle(T, ops, hp, B, n_sig, Tn, N):
+    hp.FFT_SIZE = N
+    rng = np.random.default_rng(B + Tn)
+    src = rng.random((B * n_sig, Tn, N), dtype=np.float32)
+    noise = (rng.standard_normal((B, Tn, N)) * 0.1).astype(np.float32)
+    ref = R.mix_features(src.astype(np.float64), B, n_sig, noise.astype(np.float64))
+    got = ops.mix_signals(dev(T, src), n_sig, noise=dev(T, noise))
+    assert got.shape == (B, Tn, N)
+    assert R.rel_l2(got.cpu().numpy(), ref) < 1e-6
+    mix, mix_log = ops.mix_signals(dev(T, src), n_sig, noise=dev(T, noise), log=True)
+    assert np.array_equal(mix.cpu().numpy(), got.cpu().numpy())
+    assert R.rel_l2(mix_log.cpu().numpy(), R.to_log_signal(ref)) < REL_L2
+    # no noise / device-drawn noise (reproducible with a generator, N(0, 0.1^2) like tf.random_normal(stddev=0.1))
+    assert R.rel_l2(ops.mix_signals(dev(T, src), n_sig, noise=False).cpu().numpy(), R.mix_features(src, B, n_sig)) < 1e-6
+    g1 = T.Generator(device="cuda").manual_seed(3)
+    g2 = T.Generator(device="cuda").manual_seed(3)
+    a = ops.mix_signals(dev(T, src), n_sig, generator=g1)
+    b = ops.mix_signals(dev(T, src), n_sig, generator=g2)
+    assert T.equal(a, b)
+    drawn = (a - ops.mix_signals(dev(T, src), n_sig, noise=False)).cpu().numpy()
+    assert abs(drawn.std() - 0.1) < 0.02 and abs(drawn.mean()) < 0.02
+
+
+# ---- backward kernels -------------------------------------------------------------
+def _torch_log(x, eps):
+    h = x.shape[-1] // 2
+    a2 = x[..., :h] ** 2 + x[..., h:] ** 2
+    g = 0.5 * (a2).log1p() * (a2 + eps).rsqrt()
+    return x * g.repeat(*([1] * (x.dim() - 1)), 2)
+
+
+def _torch_exp(x, eps):
+    h = x.shape[-1] // 2
+    a = (x[..., :h] ** 2 + x[..., h:] ** 2 + eps).sqrt()
+    g = a.expm1() / a
+    return x * g.repeat(*([1] * (x.dim() - 1)), 2)
+
+
+@pytest.mark.parametrize("which", ["log", "exp"])
+@pytest.mark.parametrize("scale", [1e-3, 0.3, 3.0])
+def test_log_exp_backward_matches_autograd(T, ops, hp, which, scale):
+    hp.FFT_SIZE = N = 256
+    g = T.Generator(device="cuda").manual_seed(11)
+    x = (T.randn(3, 17, N, device="cuda", generator=g) * scale).requires_grad_(True)
+    go = T.randn(3, 17, N, device="cuda", generator=g)
+    y = (ops.to_log_signal if which == "log" else ops.to_exp_signal)(x)
+    y.backward(go)
+    xd = x.detach().double().requires_grad_(True)
+    yr = (_torch_log if which == "log" else _torch_exp)(xd, hp.EPS)
+    yr.backward(go.double())
+    assert R.rel_l2(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < REL_L2
+    assert R.rel_l2(x.grad.cpu().numpy(), xd.grad.cpu().numpy()) < 2e-5
+
+
+def test_apply_mask_backward_matches_autograd(T, ops):
+    B, S, Tn, N = 2, 3, 9, 128
+    g = T.Generator(device="cuda").manual_seed(5)
+    mix = T.randn(B, Tn, N, device="cuda", generator=g).requires_grad_(True)
+    mask = T.rand(B, S, Tn, N // 2, device="cuda", generator=g).requires_grad_(True)
+    go = T.randn(B * S, Tn, N, device="cuda", generator=g)
+    ops.apply_mask(mix, mask).backward(go)
+    md, kd = mix.detach().double().requires_grad_(True), mask.detach().double().requires_grad_(True)
+    ref = (T.cat([kd, kd], dim=-1) * md[:, None]).reshape(B * S, Tn, N)
+    ref.backward(go.double())
+    assert R.rel_l2(mix.grad.cpu().numpy(), md.grad.cpu().numpy()) < 1e-6
+    assert R.rel_l2(mask.grad.cpu().numpy(), kd.grad.cpu().numpy()) < 1e-6
+
+
+# ---- demo-mode edges --------------------------------------------------------------
+@pytest.mark.parametrize("n,num", [(1000, 363), (1001, 364), (44100, 16000), (8000, 16000), (8001, 16001), (999, 500), (500, 1001)])
+def test_resample_matches_scipy(T, ops, n, num):
+    import scipy.signal
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n))
+    ref = scipy.signal.resample(x, num, axis=-1)
+    got = ops.resample(dev(T, x), num).cpu().numpy()
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-12
+    got32 = ops.resample(dev(T, x.astype(np.float32)), num).cpu().numpy()
+    assert R.rel_l2(got32, ref) < 1e-6
+    for L in (1, 255, 256, 257, 5000):
+        assert ops.resample_pad_size(L, 256) == R.resample_pad_size(L, 256)
+
+
+@pytest.mark.parametrize("rate,n,dtype", [(16000, 6000, np.int16), (8000, 3001, np.int16), (44100, 9000, np.int16),
+                                          (16000, 5000, np.float32), (22050, 5000, np.float32)])
+def test_load_save_wavfile(T, ops, hp, tmp_path, rate, n, dtype):
+    import scipy.io.wavfile
+    from gan_sass_tf_b200 import main as drv
+    hp.FFT_SIZE, hp.HOP_SIZE = 256, None
+    rng = np.random.default_rng(n + rate)
+    x = (rng.standard_normal(n) * (3000 if dtype == np.int16 else 0.1)).astype(dtype)
+    path = os.path.join(tmp_path, "in.wav")
+    scipy.io.wavfile.write(path, rate, x)
+    feat = drv.load_wavfile(path)
+    ref = R.load_wave_features(x, rate, 256)
+    assert tuple(feat.shape) == ref.shape                       # frame count bit-exact (K1, pad rule)
+    assert R.rel_l2(feat.cpu().numpy(), ref) < REL_L2
+    out = os.path.join(tmp_path, "out.wav")
+    drv.save_wavfile(out, feat)
+    sr, pcm = scipy.io.wavfile.read(out)
+    ref_pcm = R.save_wave_pcm(ref, 256)
+    assert sr == 16000 and pcm.dtype == np.int16 and pcm.shape == ref_pcm.shape
+    assert np.max(np.abs(pcm.astype(np.int32) - ref_pcm.astype(np.int32))) <= 1     # +-1 LSB at the truncation boundary
+    with pytest.raises(FileNotFoundError):
+        drv.load_wavfile(None)
+
+
+# ---- config C1: toy data, reference defaults, forward end to end -------------------
+def test_c1_toy_forward(T, ops, hp):
+    """BASELINE config C1: toy batch [24,128,256] -> mix + N(0,0.1) -> to_log -> toy separator
+    -> to_exp -> iSTFT of the 32 outputs (16 256 samples each), against the oracle chain with the
+    separator's weights evaluated in float64."""
+    from gan_sass_tf_b200.app import modules
+    from gan_sass_tf_b200.app.datasets.dataset import WhiteNoiseData
+    hp.FFT_SIZE, hp.HOP_SIZE, hp.BATCH_SIZE, hp.MAX_N_SIGNAL = 256, None, 8, 3
+    N, B, n_sig, S = 256, 8, 3, 4
+    ds = WhiteNoiseData(seed=0)
+    ds.install_and_load()
+    src = next(iter(ds.epoch('train', B * n_sig)))[0]                      # [24,128,256] uniform [0,1)
+    assert src.shape == (24, 128, 256) and src.dtype == np.float32
+    noise = (np.random.default_rng(1).standard_normal((B, 128, N)) * 0.1).astype(np.float32)
+    mix, mix_log = ops.mix_signals(dev(T, src), n_sig, noise=dev(T, noise), log=True)
+    sep_mod = modules.ToySeparator(None, 'c1/separator')
+    sep_log = sep_mod(mix_log)
+    assert tuple(sep_log.shape) == (B * S, 128, N)
+    sep = ops.to_exp_signal(sep_log)
+    waves = ops.istft(sep, N // 2)
+    assert tuple(waves.shape) == (B * S, 127 * 128)                        # 16 256 samples each
+    # oracle
+    W0 = sep_mod.p.layers['c1/separator/linear0'].weight.detach().double().cpu().numpy()
+    b0 = sep_mod.p.layers['c1/separator/linear0'].bias.detach().double().cpu().numpy()
+    W1 = sep_mod.p.layers['c1/separator/linear1'].weight.detach().double().cpu().numpy()
+    b1 = sep_mod.p.layers['c1/separator/linear1'].bias.detach().double().cpu().numpy()
+    rmix = R.mix_features(src.astype(np.float64), B, n_sig, noise.astype(np.float64))
+    rlog = R.to_log_signal(rmix)
+    h = rlog @ W0.T + b0
+    h = np.maximum(h, hp.RELU_LEAKAGE * h)
+    o = (h @ W1.T + b1).reshape(B, 128, S, N).transpose(0, 2, 1, 3).reshape(B * S, 128, N)
+    rsep = R.to_exp_signal(o)
+    rwav = R.istft_feature_np(rsep, N // 2)
+    assert R.rel_l2(mix_log.cpu().numpy(), rlog) < REL_L2
+    assert R.rel_l2(sep_log.detach().cpu().numpy(), o) < 1e-4            # fp32 matmuls of the stand-in
+    assert R.rel_l2(waves.detach().cpu().numpy(), rwav) < 1e-4
+    # metrics of main.py:353-361 / :446-457 on the same tensors
+    assert abs(float(ops.ae_loss(sep.detach(), mix, S)) - R.autoencoder_loss(rsep, rmix, B, S)) < 1e-3 * R.autoencoder_loss(rsep, rmix, B, S)
+    assert abs(float(ops.snr_metric(dev(T, src), sep.detach(), n_sig)) - R.snr_metric(src.astype(np.float64), rsep, B, n_sig)) < 1e-3
+
+
+# ---- device-resident waveform dataset ---------------------------------------------
+def test_waveform_dataset_features(T, ops, hp):
+    from gan_sass_tf_b200.app.datasets.wave import WaveformData
+    hp.FFT_SIZE, hp.HOP_SIZE = 512, 128
+    rng = np.random.default_rng(4)
+    waves = [(rng.standard_normal(int(n)) * 2000).astype(np.int16) for n in (3000, 5000, 2200, 4100, 3333, 600)]
+    ds = WaveformData()
+    ds.add_subset('train', waves)
+    seen = 0
+    for feats, frames in ds.epoch('train', 2):
+        assert feats.dim() == 3 and feats.shape[0] == 2 and feats.shape[2] == 512
+        seen += 1
+    assert seen == 3
+    feats, frames = next(iter(ds.epoch('train', 3)))
+    order = np.argsort([len(w) for w in waves], kind="stable")[:3]
+    n_max = max(max(len(waves[i]) for i in order), 512)
+    for r, i in enumerate(order):
+        x = np.zeros(n_max, np.int16)
+        x[:len(waves[i])] = waves[i]
+        assert R.rel_l2(feats[r].cpu().numpy(), R.stft_feature_np(x, 512, 128)) < REL_L2
+        assert int(frames[r]) == R.frame_count(len(waves[i]), 512, 128)[0]
+    # changing FFT_SIZE needs no re-install: the next epoch is transformed with the new size
+    hp.FFT_SIZE, hp.HOP_SIZE = 256, None
+    feats2, _ = next(iter(ds.epoch('train', 3)))
+    assert feats2.shape[2] == 256
+
+
+def test_demo_mode_writes_separated_files(T, ops, hp, tmp_path):
+    """main.py:749-771 with one clip as one batch row (A13)."""
+    import scipy.io.wavfile
+    from gan_sass_tf_b200 import main as drv
+    hp.FFT_SIZE, hp.HOP_SIZE, hp.SEPARATOR_TYPE, hp.DATASET_TYPE = 256, None, 'toy-mask', 'toy'
+    x = (np.random.default_rng(2).standard_normal(20000) * 2500).astype(np.int16)
+    path = os.path.join(tmp_path, "clip.wav")
+    scipy.io.wavfile.write(path, 16000, x)
+    drv.main(['-m', 'demo', '-if', path])
+    Tn = R.frame_count(20000, 256, 128)[0]
+    for i in range(1, hp.MAX_N_SIGNAL + 2):
+        sr, pcm = scipy.io.wavfile.read(os.path.join(tmp_path, "clip_separated_%d.wav" % i))
+        assert sr == 16000 and pcm.dtype == np.int16 and pcm.shape == ((Tn - 1) * 128,)
+        assert pcm.min() == 0 and pcm.max() >= 32766
+    res = drv.g_model.test(drv.g_dataset)
+    assert set(res) == {'SNR', 'AE'} and np.isfinite(res['SNR']) and np.isfinite(res['AE'])
