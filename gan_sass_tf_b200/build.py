@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libgss.so")
 SOURCES = ["gss_api.cu"]
-HEADERS = ["gss_fft.cuh", "gss_stream.cuh", "gss_elem.cuh", os.path.join("..", "..", "include", "gss_api.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "gss_api.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -14,6 +14,7 @@
 #include "gss_elem.cuh"
 #include "gss_generic.cuh"
 #include "gss_stream.cuh"
+#include "gss_team.cuh"
 
 namespace {
 
@@ -46,8 +47,22 @@ int sm_count() {
     return sms[dev];
 }
 
+// kernel families: 0 = automatic (N = 512: register-exchange streaming kernels of gss_stream.cuh; other sizes:
+// the shared-memory-FFT streaming kernels of gss_team.cuh; whatever those do not cover: gss_generic.cuh),
+// 1 = never the N = 512 register kernels, 2 = gss_generic.cuh only (cross-check paths for the tests)
 std::atomic<int> g_force_generic{0};
 bool fast_n(int N) { return N == 512 && !g_force_generic.load(std::memory_order_relaxed); }   // register-streaming kernels
+// hop in slots for the team kernels, 0 when (N, H) is not covered
+int team_hs(int N, int H) {
+    if (g_force_generic.load(std::memory_order_relaxed) >= 2) return 0;
+    int slot = 0;
+    switch (N) { case 256: slot = 64; break; case 512: slot = 128; break; case 1024: slot = 256; break;
+                 case 2048: slot = 512; break; case 4096: slot = 512; break; default: return 0; }
+    if (H % slot) return 0;
+    const int hs = H / slot, fs = N / slot;
+    if (hs < 1 || fs % hs || fs / hs < 2) return 0;
+    return hs;
+}
 bool supported_n(int N) { return N >= 64 && N <= 4096 && !(N & (N - 1)); }  // the rest: shared-memory FFT
 
 int check_nh(int N, int H, int* hs) {
@@ -134,6 +149,64 @@ int launch_ola_generic(gss::gen::OlaArgs a, cudaStream_t st) {
     return after_launch("gen::ola_kernel");
 }
 
+// ---- team path (gss_team.cuh) -------------------------------------------------------
+template <typename K>
+int64_t cta_slots(K kernel, int threads, size_t smem) {
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    return (int64_t)sm_count() * nb;
+}
+template <int N> size_t team_bytes(int nbuf) { return sizeof(float2) * (size_t)nbuf * (N + N / 16); }
+
+template <int N, int HS, typename TIn>
+int team_stft(gss::team::StftArgs<TIn> a, cudaStream_t st) {
+    auto k = gss::team::stft_kernel<N, HS, TIn>;
+    const size_t smem = team_bytes<N>(2);
+    if (int rc = prep(k, smem)) return rc;
+    gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, cta_slots(k, gss::team::Plan<N>::TPT, smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    k<<<(unsigned)(a.B * a.nchunk), gss::team::Plan<N>::TPT, smem, st>>>(a);
+    return after_launch("team::stft_kernel");
+}
+template <int N, int HS>
+int team_istft(gss::team::IstftArgs a, cudaStream_t st) {
+    auto k = gss::team::istft_kernel<N, HS>;
+    const size_t smem = team_bytes<N>(2);
+    if (int rc = prep(k, smem)) return rc;
+    gss::ChunkPlan pl = plan_chunks(a.rows, a.npairs, gss::team::TGeo<N, HS>::HALO, cta_slots(k, gss::team::Plan<N>::TPT, smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    k<<<(unsigned)(a.rows * a.nchunk), gss::team::Plan<N>::TPT, smem, st>>>(a);
+    return after_launch("team::istft_kernel");
+}
+template <int N, int HS, int ST>
+int team_synth_st(gss::team::SynthArgs a, cudaStream_t st) {
+    auto k = gss::team::mask_istft_kernel<N, HS, ST>;
+    const size_t smem = team_bytes<N>(3);
+    if (int rc = prep(k, smem)) return rc;
+    a.ngroups = (a.S + ST - 1) / ST;
+    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::team::TGeo<N, HS>::HALO, cta_slots(k, gss::team::Plan<N>::TPT, smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    k<<<(unsigned)(a.B * a.ngroups * a.nchunk), gss::team::Plan<N>::TPT, smem, st>>>(a);
+    return after_launch("team::mask_istft_kernel");
+}
+template <int N, int HS>
+int team_synth(gss::team::SynthArgs a, cudaStream_t st) {
+    if (a.S % 3 == 0) return team_synth_st<N, HS, 3>(a, st);
+    if (a.S % 2 == 0) return team_synth_st<N, HS, 2>(a, st);
+    if (a.S == 1) return team_synth_st<N, HS, 1>(a, st);
+    return team_synth_st<N, HS, 3>(a, st);
+}
+// F<N, HS>::run(args...) for the (N, hs) pairs the team kernels cover
+#define GSS_TEAM_DISPATCH(N, hs, CALL)                                                        \
+    do {                                                                                      \
+        if (N == 256 && hs == 1) { CALL(256, 1) } if (N == 256 && hs == 2) { CALL(256, 2) }     \
+        if (N == 512 && hs == 1) { CALL(512, 1) } if (N == 512 && hs == 2) { CALL(512, 2) }     \
+        if (N == 1024 && hs == 1) { CALL(1024, 1) } if (N == 1024 && hs == 2) { CALL(1024, 2) } \
+        if (N == 2048 && hs == 1) { CALL(2048, 1) } if (N == 2048 && hs == 2) { CALL(2048, 2) } \
+        if (N == 4096 && hs == 1) { CALL(4096, 1) } if (N == 4096 && hs == 2) { CALL(4096, 2) } \
+        if (N == 4096 && hs == 4) { CALL(4096, 4) }                                             \
+    } while (0)
+
 // ---- STFT ---------------------------------------------------------------
 template <int N, int HS, bool LOG, typename TIn, int WARPS = 4>
 int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
@@ -179,7 +252,17 @@ int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int 
     if (int rc = frame_count(n, N, H, &a.T, nullptr)) return rc;
     a.npairs = (int)((a.T + 1) / 2);
     cudaStream_t st = (cudaStream_t)stream;
-    if (!fast_n(N)) return launch_stft_generic<TIn>(wave, B, n, ld, a.T, N, H, flags, eps, feat, st);
+    if (!fast_n(N)) {
+        if (const int ths = team_hs(N, H)) {
+            gss::team::StftArgs<TIn> t{};
+            t.wave = wave; t.feat = feat; t.B = B; t.n = n; t.ld = ld; t.T = a.T; t.npairs = a.npairs; t.al_in = a.al_in;
+            t.log = (flags & GSS_FLAG_LOG) ? 1 : 0; t.eps = eps;
+#define GSS_CALL(NN, HH) return team_stft<NN, HH, TIn>(t, st);
+            GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
+#undef GSS_CALL
+        }
+        return launch_stft_generic<TIn>(wave, B, n, ld, a.T, N, H, flags, eps, feat, st);
+    }
     const bool lg = flags & GSS_FLAG_LOG;
 #define GSS_CASE(NN, HH) if (N == NN && hs == HH) return lg ? launch_stft<NN, HH, true, TIn>(a, st) : launch_stft<NN, HH, false, TIn>(a, st);
     GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
@@ -333,7 +416,7 @@ int gss_version(void) { return 100; }
 const char* gss_last_error(void) { return g_err.c_str(); }
 int64_t gss_launch_count(void) { return g_launches.load(); }
 int gss_set_path(int path) {
-    if (path != 0 && path != 1) return fail(GSS_EINVAL, "set_path: 0 = automatic, 1 = any-size shared-memory kernels only");
+    if (path < 0 || path > 2) return fail(GSS_EINVAL, "set_path: 0 = automatic, 1 = no register-exchange kernels, 2 = gss_generic.cuh only");
     g_force_generic.store(path);
     return GSS_OK;
 }
@@ -366,6 +449,14 @@ int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H, int 
     a.npairs = (int)((T + 1) / 2);
     cudaStream_t st = (cudaStream_t)stream;
     if (!fast_n(N)) {
+        if (const int ths = team_hs(N, H)) {
+            gss::team::IstftArgs t{};
+            t.feat = feat; t.out = wave_out; t.rows = R; t.T = T; t.ld_out = ld_out; t.npairs = a.npairs; t.al_out = a.al_out;
+            t.exp = (flags & GSS_FLAG_EXP) ? 1 : 0; t.eps = eps;
+#define GSS_CALL(NN, HH) return team_istft<NN, HH>(t, st);
+            GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
+#undef GSS_CALL
+        }
         gss::gen::OlaArgs g{};
         g.feat = feat; g.out = wave_out; g.rows = R; g.T = T; g.ld_out = ld_out; g.N = N; g.H = H; g.S = 1;
         g.exp = (flags & GSS_FLAG_EXP) ? 1 : 0; g.eps = eps;
@@ -396,6 +487,14 @@ int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64
     a.npairs = (int)((a.T + 1) / 2);
     cudaStream_t st = (cudaStream_t)stream;
     if (!fast_n(N)) {
+        if (const int ths = team_hs(N, H)) {
+            gss::team::SynthArgs t{};
+            t.wave = wave; t.mask = mask; t.out = out; t.B = B; t.n = n; t.ld = ld; t.T = a.T; t.ld_out = ld_out; t.S = S;
+            t.npairs = a.npairs; t.al_in = a.al_in; t.al_out = a.al_out;
+#define GSS_CALL(NN, HH) return team_synth<NN, HH>(t, st);
+            GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
+#undef GSS_CALL
+        }
         gss::gen::OlaArgs g{};
         g.wave = wave; g.mask = mask; g.out = out; g.rows = B * S; g.n = n; g.ld = ld; g.T = a.T; g.ld_out = ld_out;
         g.N = N; g.H = H; g.S = S;

@@ -223,8 +223,8 @@ def test_apply_mask_matches_oracle(T, ops):
 
 
 def test_streaming_and_generic_paths_agree(T, ops):
-    """N = 512 has two independent implementations (register-streaming FFT, shared-memory
-    Stockham FFT): same inputs, results within float32 rounding of each other."""
+    """N = 512 has three independent implementations (register-exchange streaming FFT, shared-memory
+    Stockham team FFT, the per-frame fallback): same inputs, results within float32 rounding."""
     from gan_sass_tf_b200 import _native
     N, H, n, B, S = 512, 128, 9000, 3, 3
     rng = np.random.default_rng(77)
@@ -233,14 +233,43 @@ def test_streaming_and_generic_paths_agree(T, ops):
     m = dev(T, rng.random((B, S, Tn, N // 2)).astype(np.float32))
     fast = (ops.stft(x, N, H), ops.stft_log(x, N, H), ops.mask_istft(x, m, N, H))
     fast += (ops.istft(fast[0], H),)
-    try:
-        _native.set_path(1)
-        slow = (ops.stft(x, N, H), ops.stft_log(x, N, H), ops.mask_istft(x, m, N, H))
-        slow += (ops.istft(fast[0], H),)
-    finally:
-        _native.set_path(0)
-    for a, b in zip(fast, slow):
-        assert R.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+    for path in (1, 2):
+        try:
+            _native.set_path(path)
+            slow = (ops.stft(x, N, H), ops.stft_log(x, N, H), ops.mask_istft(x, m, N, H))
+            slow += (ops.istft(fast[0], H),)
+        finally:
+            _native.set_path(0)
+        for a, b in zip(fast, slow):
+            assert R.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6, f"path {path}"
+
+
+@pytest.mark.parametrize("N,H", [(256, 64), (256, 128), (1024, 256), (1024, 512), (2048, 512), (2048, 1024),
+                                 (4096, 512), (4096, 1024), (4096, 2048)])
+def test_team_kernels_all_sizes(T, ops, N, H):
+    """every (N, hop) the shared-memory team kernels cover: all three ops against the oracle, ragged length,
+    several chunks per row (long rows), S = 1..4, and the per-frame fallback as a second opinion."""
+    from gan_sass_tf_b200 import _native
+    rng = np.random.default_rng(N + H)
+    for n, B, S in ((N, 1, 1), (3 * N + 17, 2, 2), (40 * N + 2 * H + 5, 2, 3), (9 * N, 1, 4)):
+        x = speechish(rng, B, n)
+        Tn, _ = R.frame_count(n, N, H)
+        mask = rng.random((B, S, Tn, N // 2)).astype(np.float32)
+        xd, md = dev(T, x), dev(T, mask)
+        f = ops.stft(xd, N, H)
+        ref_f = R.stft_feature_np(x, N, H)
+        assert tuple(f.shape) == ref_f.shape
+        assert R.rel_l2(f.cpu().numpy(), ref_f) < REL_L2
+        assert R.rel_l2(ops.stft_log(xd, N, H).cpu().numpy(), R.to_log_signal(ref_f)) < REL_L2
+        y = ops.mask_istft(xd, md, N, H).cpu().numpy()
+        assert R.rel_l2(y, R.mask_istft_np(x, mask, N, H).reshape(B * S, -1)) < REL_L2
+        w = ops.istft(f, H).cpu().numpy()
+        assert R.snr_db(x, w[:, :n]) >= 100.0
+        try:
+            _native.set_path(2)
+            assert R.rel_l2(ops.mask_istft(xd, md, N, H).cpu().numpy(), y) < 2e-6
+        finally:
+            _native.set_path(0)
 
 
 # --------------------------------------------------------------------------
