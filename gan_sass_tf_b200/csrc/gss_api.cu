@@ -109,6 +109,26 @@ constexpr int WARPS = 4;
 template <int N>
 size_t team_smem(int warps) { return sizeof(float) * ((size_t)warps * gss::Geo<N>::TEAM_FLOATS); }
 
+// Lane-constant table of the register-exchange kernels (gss_fft.cuh), filled once per device.  The fill
+// runs on the stream of the first call, followed by one stream synchronisation, so the table is visible
+// to every later launch on any stream; inside a stream capture it is simply recorded into the graph.
+// Not counted by gss_launch_count() (set-up, not one of the path's kernels).
+int ensure_tables(cudaStream_t st) {
+    static std::atomic<int> ready[64];
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(GSS_EUNSUPPORTED, "device ordinal %d out of range", dev);
+    if (ready[dev].load(std::memory_order_acquire)) return GSS_OK;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    gss::tables_kernel<512><<<1, 32, 0, st>>>();
+    CK(cudaGetLastError());
+    if (cap != cudaStreamCaptureStatusNone) return GSS_OK;
+    CK(cudaStreamSynchronize(st));
+    ready[dev].store(1, std::memory_order_release);
+    return GSS_OK;
+}
+
 template <typename K>
 int prep(K kernel, size_t smem) {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -213,6 +233,7 @@ int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
     auto k = gss::stft_kernel<N, HS, LOG, TIn, WARPS>;
     const size_t smem = team_smem<N>(WARPS);
     if (int rc = prep(k, smem)) return rc;
+    if (int rc = ensure_tables(st)) return rc;
     gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, team_slots(k, WARPS, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.B * a.nchunk;
@@ -276,6 +297,7 @@ int launch_istft(gss::IstftArgs a, cudaStream_t st) {
     auto k = gss::istft_kernel<N, HS, EXP, WARPS>;
     const size_t smem = team_smem<N>(WARPS);
     if (int rc = prep(k, smem)) return rc;
+    if (int rc = ensure_tables(st)) return rc;
     gss::ChunkPlan pl = plan_chunks(a.rows, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.rows * a.nchunk;
@@ -292,6 +314,7 @@ int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
     smem += (size_t)tune("GSS_EXTRA_SMEM", 0);      // occupancy limiter for single-warp-per-SMSP experiments
 #endif
     if (int rc = prep(k, smem)) return rc;
+    if (int rc = ensure_tables(st)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
     { static int stg = -1; if (stg < 0) { const char* v = getenv("GSS_STAGGER"); stg = v ? atoi(v) : 0; } a.stagger = stg; }
 #ifdef GSS_TIMING

@@ -174,6 +174,52 @@ __device__ __forceinline__ void team_init(TeamCtx<N>& c, int j, float* team_smem
     }
 }
 
+// Per-device table of the lane constants (pass-0 twiddles, middle twiddles, Hann window at the lane's
+// sample positions), filled once by tables_kernel: a team then starts with 28 coalesced 8-byte loads
+// instead of ~36 sincospif / cospif evaluations per thread (about two frame pairs' worth of
+// instructions, paid by every work item).  Same code computes the values, so results are bit-identical.
+constexpr int TAB_TW0 = 0;        // [k0-1][re/im] : 14 rows
+constexpr int TAB_TW1 = 14;       // [b][re/im]    : 6 rows
+constexpr int TAB_WIN = 20;       // [n0]          : 8 rows (unscaled periodic Hann at samples 2j+e + L*n0)
+constexpr int TAB_ROWS = 28;
+__device__ v2 g_lane_tab[TAB_ROWS][32];
+
+template <int N>
+__global__ void tables_kernel() {
+    const int j = threadIdx.x;
+    TeamCtx<N> c;
+    team_init<N>(c, j, nullptr);
+#pragma unroll
+    for (int k0 = 1; k0 < 8; ++k0) { g_lane_tab[TAB_TW0 + 2 * (k0 - 1)][j] = c.tw0[k0].re; g_lane_tab[TAB_TW0 + 2 * (k0 - 1) + 1][j] = c.tw0[k0].im; }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) { g_lane_tab[TAB_TW1 + 2 * b][j] = c.tw1[b].re; g_lane_tab[TAB_TW1 + 2 * b + 1][j] = c.tw1[b].im; }
+#pragma unroll
+    for (int n0 = 0; n0 < 8; ++n0) {
+        const int i0 = 2 * j + Geo<N>::L * n0;
+        g_lane_tab[TAB_WIN + n0][j] = make_float2(0.5f - 0.5f * cospif(2.0f * (float)i0 / (float)N),
+                                                  0.5f - 0.5f * cospif(2.0f * (float)(i0 + 1) / (float)N));
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void team_init_tab(TeamCtx<N>& c, int j, float* team_smem) {
+    typedef Geo<N> G;
+    c.j = j;
+    c.cA = j ? j : 0;
+    c.cB = j ? G::L - j : G::L / 2;
+    c.e0 = reinterpret_cast<v2*>(team_smem);
+    c.e1 = team_smem + G::E0_F4 * 4;
+#pragma unroll
+    for (int k0 = 1; k0 < 8; ++k0) { c.tw0[k0].re = g_lane_tab[TAB_TW0 + 2 * (k0 - 1)][j]; c.tw0[k0].im = g_lane_tab[TAB_TW0 + 2 * (k0 - 1) + 1][j]; }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) { c.tw1[b].re = g_lane_tab[TAB_TW1 + 2 * b][j]; c.tw1[b].im = g_lane_tab[TAB_TW1 + 2 * b + 1][j]; }
+}
+// analysis / synthesis window (scaled) at this lane's sample positions, from the table
+__device__ __forceinline__ void window_tab(int j, float scale, v2 (&w)[8]) {
+#pragma unroll
+    for (int n0 = 0; n0 < 8; ++n0) w[n0] = vmul(g_lane_tab[TAB_WIN + n0][j], vset(scale));
+}
+
 // ---------------------------------------------------------------------------
 // forward: a[n0] (lanes e=0,1: samples 2j+e + L*n0; re = sequence a, im = sequence b)
 //       -> a[k2] (lanes A,B: Z[cA + L*k2], Z[cB + L*k2]).  Z[k] and Z[N-k] sit in the same

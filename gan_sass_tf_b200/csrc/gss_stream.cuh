@@ -337,9 +337,9 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((6
     const bool t0 = j == 0;
 
     TeamCtx<N> ctx;
-    team_init<N>(ctx, j, smf + warp * G::TEAM_FLOATS);
+    team_init_tab<N>(ctx, j, smf + warp * G::TEAM_FLOATS);
     v2 win[8];
-    make_window<SG>(j, 1.0f / (float)N, win);      // 1/sum(w) = 2/N, and the 1/2 of the two-for-one split
+    window_tab(j, 1.0f / (float)N, win);           // 1/sum(w) = 2/N, and the 1/2 of the two-for-one split
 
     const TIn* row = p.wave + b * p.ld;
     const bool al = p.al_in != 0;
@@ -461,10 +461,10 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     const bool t0 = j == 0;
 
     TeamCtx<N> ctx;
-    team_init<N>(ctx, j, smf + warp * G::TEAM_FLOATS);
+    team_init_tab<N>(ctx, j, smf + warp * G::TEAM_FLOATS);
     v2 win[8];
     // frame = sum(w) * irfft = (N/2)(1/N) * raw inverse: the 1/2 and 1/sum(w^2) are applied at the store
-    make_window<SG>(j, 1.0f, win);
+    window_tab(j, 1.0f, win);
     OlaOut<SG> o;
     o.init(p.T, j, p.al_out != 0, 1.0f);
     float* orow = p.out + r * p.ld_out;
@@ -613,9 +613,9 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
         while (clock64() < tgo) { }
     }
     TeamCtx<N> ctx;
-    team_init<N>(ctx, j, team);
+    team_init_tab<N>(ctx, j, team);
     v2 win[8];                                     // hann / N: analysis scale; synthesis rescaled at the store
-    make_window<SG>(j, 1.0f / (float)N, win);
+    window_tab(j, 1.0f / (float)N, win);
 
     OlaOut<SG> o;
     o.init(p.T, j, p.al_out != 0, (float)N);
