@@ -309,7 +309,7 @@ def run_native(args):
     if rank == 0:
         audio_s = B * n / SR
         value = world * args.steps * audio_s / (total_ms * 1e-3)
-        e2e_val = world * e2e_steps * audio_s / (e2e_ms * 1e-3)
+        e2e_val = None if e2e_ms != e2e_ms else world * e2e_steps * audio_s / (e2e_ms * 1e-3)
         stft_b, synth_b = algorithmic_bytes(B, n, N, H, S)
         peaks = {}
         try:
@@ -338,7 +338,7 @@ def run_native(args):
                          "stft_kernel": {"bytes_per_launch": stft_b, "ms_per_launch": stft_ms,
                                          "achieved": stft_b / (stft_ms * 1e-3) / 1e9}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "steps": e2e_steps, "ms_per_step": None if e2e_ms != e2e_ms else e2e_ms / e2e_steps,
                     "api": "SpectralPipeline.analyse/synthesise(block=False)/wait, depth 2 -> gss_stft_h2d_async / gss_mask_istft_d2h_async / gss_wait_host "
                            "(pinned host buffers; host clock between device syncs)"},
             "gpu_launches": int(launches),
