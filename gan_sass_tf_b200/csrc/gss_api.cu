@@ -15,6 +15,7 @@
 #include "gss_generic.cuh"
 #include "gss_stream.cuh"
 #include "gss_team.cuh"
+#include "gss_split.cuh"
 
 namespace {
 
@@ -359,8 +360,33 @@ int launch_synth(gss::SynthArgs a, cudaStream_t st) {
 #endif
     return launch_synth_w<N, HS, ST, 4>(a, st);
 }
+// role-split variant (gss_split.cuh): one CTA of 1 + ST warps per (row, source group, chunk)
+template <int N, int HS, int ST>
+int launch_synth_split(gss::SynthArgs a, cudaStream_t st) {
+    auto k = gss::mask_istft_split_kernel<N, HS, ST>;
+    const size_t smem = gss::SplitSmem<N, ST>::bytes();
+    if (int rc = prep(k, smem)) return rc;
+    if (int rc = ensure_tables(st)) return rc;
+    a.ngroups = (a.S + ST - 1) / ST;
+    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, cta_slots(k, (1 + ST) * 32, smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    k<<<(unsigned)(a.B * a.ngroups * a.nchunk), (1 + ST) * 32, smem, st>>>(a);
+    return after_launch("mask_istft_split_kernel");
+}
+int synth_variant() {       // 0 = one warp per pair (gss_stream.cuh), 1 = role-split CTAs (gss_split.cuh)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GSS_SYNTH_SPLIT"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 template <int N, int HS>
 int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
+    if (synth_variant() == 1) {
+        if (a.S % 3 == 0) return launch_synth_split<N, HS, 3>(a, st);
+        if (a.S % 2 == 0) return launch_synth_split<N, HS, 2>(a, st);
+        if (a.S == 1) return launch_synth_split<N, HS, 1>(a, st);
+        return launch_synth_split<N, HS, 3>(a, st);
+    }
     // sources carried per pass: 3 when S is a multiple of 3, else 2 (S even) or 1
     if (a.S % 3 == 0) return launch_synth<N, HS, 3>(a, st);
     if (a.S % 4 == 0 && HS == 2) return launch_synth<N, HS, 4>(a, st);

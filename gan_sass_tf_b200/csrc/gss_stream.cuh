@@ -92,6 +92,21 @@ __device__ __forceinline__ float exp_gain(float re, float im, float eps) {
     float a = sqrtf(fmaf(re, re, fmaf(im, im, eps)));
     return expm1f(a) / a;
 }
+// to_exp gain inside the fused iSTFT prologue, two bins at once, valid for a = sqrt(a2e) < 1 (a2e = re^2 +
+// im^2 + eps): expm1(a)/a as its Taylor series (next term a^10/11! < 2.6e-8), a through rsqrt.  Chosen per warp
+// (one vote); larger magnitudes take the libm path.  The stand-alone to_exp kernel (gss_to_exp) keeps libm.
+__device__ __forceinline__ v2 exp_gain2_small(v2 a2e) {
+    const v2 a = vmul(a2e, make_float2(rsqrtf(a2e.x), rsqrtf(a2e.y)));
+    v2 p = vfma(a, vset(1.0f / 3628800.0f), vset(1.0f / 362880.0f));
+    p = vfma(p, a, vset(1.0f / 40320.0f));
+    p = vfma(p, a, vset(1.0f / 5040.0f));
+    p = vfma(p, a, vset(1.0f / 720.0f));
+    p = vfma(p, a, vset(1.0f / 120.0f));
+    p = vfma(p, a, vset(1.0f / 24.0f));
+    p = vfma(p, a, vset(1.0f / 6.0f));
+    p = vfma(p, a, vset(0.5f));
+    return vfma(p, a, vset(1.0f));
+}
 // two bins at once, valid for a2 <= 1 (always true for waveforms in [-1, 1]: |X0| + |X_nyq| <= 1
 // and |X_k| <= 1 under scaling='spectrum'):  0.5*log1p(x) = atanh(s), s = x / (2 + x) <= 1/3,
 // atanh(s) = s * sum_k s^2k / (2k+1); truncated after k = 6 (next term < 1.5e-8 relative).
@@ -304,6 +319,14 @@ __device__ __forceinline__ v2 half_log1p_over_x(v2 x) {
     p = vfma(p, x, vset(4.999999998e-01f));
     return p;
 }
+// a2 <= 1/64 (ordinary audio levels: |X|^2 ~ 1e-4): three Taylor terms, next term x^4/10 < 1.2e-8 relative
+__device__ __forceinline__ v2 log_gain2_micro(v2 a2, float eps) {
+    v2 p = vfma(a2, vset(-0.125f), vset(1.0f / 6.0f));
+    p = vfma(p, a2, vset(-0.25f));
+    p = vfma(p, a2, vset(0.5f));
+    v2 e = vadd(a2, vset(eps));
+    return vmul(vmul(a2, p), make_float2(rsqrtf(e.x), rsqrtf(e.y)));
+}
 // to_log gain for two bins with a2 <= 1/4: a2 * (0.5*log1p(a2)/a2) * rsqrt(a2 + eps)
 __device__ __forceinline__ v2 log_gain2_tiny(v2 a2, float eps) {
     v2 e = vadd(a2, vset(eps));
@@ -383,8 +406,14 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((6
                 a2b[i] = vfma(s.br[i], s.br[i], vmul(s.bi[i], s.bi[i]));
                 mx = fmaxf(fmaxf(mx, fmaxf(a2a[i].x, a2a[i].y)), fmaxf(a2b[i].x, a2b[i].y));
             }
-            const bool tiny = __all_sync(0xffffffffu, mx <= 0.25f);
-            if (tiny) {
+            if (__all_sync(0xffffffffu, mx <= 0.015625f)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v2 ga = log_gain2_micro(a2a[i], p.eps), gb = log_gain2_micro(a2b[i], p.eps);
+                    s.ar[i] = vmul(s.ar[i], ga); s.ai[i] = vmul(s.ai[i], ga);
+                    s.br[i] = vmul(s.br[i], gb); s.bi[i] = vmul(s.bi[i], gb);
+                }
+            } else if (__all_sync(0xffffffffu, mx <= 0.25f)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     v2 ga = log_gain2_tiny(a2a[i], p.eps), gb = log_gain2_tiny(a2b[i], p.eps);
@@ -491,12 +520,32 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
             } else {
                 ybr[i] = make_float2(0.f, 0.f); ybi[i] = make_float2(0.f, 0.f);
             }
-            if (EXP) {
-                float g;
-                g = exp_gain(yar[i].x, yai[i].x, p.eps); yar[i].x *= g; yai[i].x *= g;
-                g = exp_gain(yar[i].y, yai[i].y, p.eps); yar[i].y *= g; yai[i].y *= g;
-                g = exp_gain(ybr[i].x, ybi[i].x, p.eps); ybr[i].x *= g; ybi[i].x *= g;
-                g = exp_gain(ybr[i].y, ybi[i].y, p.eps); ybr[i].y *= g; ybi[i].y *= g;
+        }
+        if (EXP) {
+            v2 ea[4], eb[4];
+            float mx = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ea[i] = vfma(yar[i], yar[i], vfma(yai[i], yai[i], vset(p.eps)));
+                eb[i] = vfma(ybr[i], ybr[i], vfma(ybi[i], ybi[i], vset(p.eps)));
+                mx = fmaxf(fmaxf(mx, fmaxf(ea[i].x, ea[i].y)), fmaxf(eb[i].x, eb[i].y));
+            }
+            if (__all_sync(0xffffffffu, mx < 1.0f)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const v2 ga = exp_gain2_small(ea[i]), gb = exp_gain2_small(eb[i]);
+                    yar[i] = vmul(yar[i], ga); yai[i] = vmul(yai[i], ga);
+                    ybr[i] = vmul(ybr[i], gb); ybi[i] = vmul(ybi[i], gb);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float g;
+                    g = exp_gain(yar[i].x, yai[i].x, p.eps); yar[i].x *= g; yai[i].x *= g;
+                    g = exp_gain(yar[i].y, yai[i].y, p.eps); yar[i].y *= g; yai[i].y *= g;
+                    g = exp_gain(ybr[i].x, ybi[i].x, p.eps); ybr[i].x *= g; ybi[i].x *= g;
+                    g = exp_gain(ybr[i].y, ybi[i].y, p.eps); ybr[i].y *= g; ybi[i].y *= g;
+                }
             }
         }
         cv2 a[8];

@@ -70,3 +70,20 @@ def test_ops_reject_cpu_tensors(native):
         ops.stft(torch.zeros(1, 4000), 512, 128)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.to_log_signal(torch.zeros(1, 4, 256))
+
+
+def test_plain_c_consumer(native, tmp_path):
+    """include/gss_api.h compiles as C and a gcc-built program links libgss.so and gets the same answers."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = os.path.join(tmp_path, "abi_smoke")
+    libdir = os.path.dirname(native.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe,
+                    "-L", libdir, "-lgss", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi_smoke ok" in r.stdout
