@@ -269,6 +269,8 @@ def run_native(args):
         hbuf.copy_(waves[0].cpu())
     e2e_steps = max(4, min(args.steps, 20))
     e2e_ms = float("nan")
+    e2e16_ms = float("nan")
+    pipe_f32_bytes = (pipe.h2d_bytes, pipe.d2h_bytes)
     e2e_checksum = 0.0
     if not args.no_e2e:
         def e2e_run(steps):
@@ -288,6 +290,19 @@ def run_native(args):
         e2e_checksum = e2e_run(e2e_steps)
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - tw0) * 1e3
+        # the same loop with int16 PCM on the host link (the WAV sample format the reference reads and writes:
+        # main.py:83, :112-116): half the bytes each way.  Reported beside e2e, not instead of it.
+        del pipe
+        pipe16 = SpectralPipeline(B, n, S, N, H, device=dev, chunks=8, depth=2, pcm16=True)
+        for hbuf in pipe16.wave_hs:
+            hbuf.copy_((waves[0] * 32767.0).to(torch.int16).cpu())
+        pipe, pipe_f32_bytes = pipe16, (B * n * 4, B * S * L * 4)
+        e2e_run(max(2, min(args.warmup, 4)))
+        barrier()
+        tw0 = time.perf_counter()
+        e2e_run(e2e_steps)
+        torch.cuda.synchronize()
+        e2e16_ms = (time.perf_counter() - tw0) * 1e3
 
     # ---- untimed full-size property check + the metric all-reduce (the only collective) ----
     from gan_sass_tf_b200.app import parallel
@@ -301,10 +316,10 @@ def run_native(args):
     vec = parallel.metric_vector(float(snr.sum()), 0.0, float(snr.sum()), float(nchk), device=dev)
     recon_snr_db, _, _, checked = parallel.allreduce_metrics(vec)
 
-    t = torch.tensor([total_ms, e2e_ms, stft_ms, synth_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([total_ms, e2e_ms, stft_ms, synth_ms, e2e16_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, stft_ms, synth_ms = (float(v) for v in t.tolist())
+    total_ms, e2e_ms, stft_ms, synth_ms, e2e16_ms = (float(v) for v in t.tolist())
 
     if rank == 0:
         audio_s = B * n / SR
@@ -337,10 +352,14 @@ def run_native(args):
                          "step_frac_of_hbm": (stft_b + synth_b) / (total_ms / args.steps * 1e-3) / 1e9 / peak,
                          "stft_kernel": {"bytes_per_launch": stft_b, "ms_per_launch": stft_ms,
                                          "achieved": stft_b / (stft_ms * 1e-3) / 1e9}},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": pipe_f32_bytes[0], "d2h_bytes_per_step": pipe_f32_bytes[1],
                     "steps": e2e_steps, "ms_per_step": None if e2e_ms != e2e_ms else e2e_ms / e2e_steps,
                     "api": "SpectralPipeline.analyse/synthesise(block=False)/wait, depth 2 -> gss_stft_h2d_async / gss_mask_istft_d2h_async / gss_wait_host "
                            "(pinned host buffers; host clock between device syncs)"},
+            "e2e_pcm16": None if e2e16_ms != e2e16_ms else {
+                "value": world * e2e_steps * audio_s / (e2e16_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e16_ms / e2e_steps,
+                "h2d_bytes_per_step": B * n * 2, "d2h_bytes_per_step": B * S * L * 2,
+                "what": "same loop, int16 PCM in / per-clip normalised int16 PCM out (SpectralPipeline(pcm16=True))"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"recon_snr_db": recon_snr_db, "recon_snr_db_no_eps": true_snr_db, "e2e_checksum": e2e_checksum, "utterances": int(checked),

@@ -43,6 +43,8 @@ SIGNATURES = {
     "gss_stft_h2d_async": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int, _P]),
     "gss_mask_istft_d2h_async": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, _P, _P, c_int64, c_int, _P]),
     "gss_wait_host": (c_int, [_P]),
+    "gss_stft_h2d_i16_async": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int, _P]),
+    "gss_mask_istft_d2h_pcm16_async": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, c_int64, c_int, _P]),
     "gss_mix_features": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, c_float, _P, _P, _P]),
     "gss_to_log_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P]),
     "gss_to_exp_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P]),

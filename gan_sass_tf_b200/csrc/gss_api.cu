@@ -747,6 +747,69 @@ int gss_mask_istft_d2h_async(const float* wave_d, const float* mask_d, int64_t B
     return GSS_OK;
 }
 
+// int16 PCM on the host link in both directions (what the WAV files of main.py:83 / :116 hold): half the
+// bytes of the float32 forms.  Upload: pcm_h -> pcm_d (int16) -> features straight from the int16 samples
+// (gss_stft_packed_i16) and a float32 copy wave_d for the synthesis stage.  Download: separated waveforms ->
+// per-row min/max normalisation to int16 (main.py:112-116) -> pcm_h.
+int gss_stft_h2d_i16_async(const int16_t* pcm_h, int16_t* pcm_d, float* wave_d, int64_t B, int64_t n, int64_t ld, int N, int H,
+                           int flags, float eps, float* feat_d, int chunks, void* stream) {
+    int64_t T = 0;
+    if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
+    if (!pcm_h || !pcm_d || !wave_d || !feat_d) return fail(GSS_EINVAL, "stft_h2d_i16: null pointer");
+    if (chunks < 1 || ld < n) return fail(GSS_EINVAL, "stft_h2d_i16: bad chunks/ld");
+    if (int rc = g_cs.init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaEventRecord(g_cs.order, st));
+    CK(cudaStreamWaitEvent(g_cs.h2d, g_cs.order, 0));
+    const int64_t per = (B + chunks - 1) / chunks;
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
+        const int64_t nb = (B - b0 < per) ? B - b0 : per;
+        CK(cudaMemcpy2DAsync(pcm_d + b0 * ld, sizeof(int16_t) * ld, pcm_h + b0 * n, sizeof(int16_t) * n, sizeof(int16_t) * n, nb,
+                             cudaMemcpyHostToDevice, g_cs.h2d));
+        cudaEvent_t ev = g_cs.ev[k % 8];
+        CK(cudaEventRecord(ev, g_cs.h2d));
+        CK(cudaStreamWaitEvent(st, ev, 0));
+        if (int rc = gss_stft_packed_i16(pcm_d + b0 * ld, nb, n, ld, N, H, flags, eps, feat_d + b0 * T * N, stream)) return rc;
+        gss::i16_to_f32_kernel<<<grid_for(nb * ld, 256), 256, 0, st>>>(pcm_d + b0 * ld, wave_d + b0 * ld, nb * ld);
+        if (int rc = after_launch("i16_to_f32_kernel")) return rc;
+    }
+    return GSS_OK;
+}
+
+int gss_mask_istft_d2h_pcm16_async(const float* wave_d, const float* mask_d, int64_t B, int S, int64_t n, int64_t ld, int N, int H,
+                                   float* out_d, float* minmax_d, int16_t* pcm_d, int16_t* pcm_h, int64_t ld_out, int chunks,
+                                   void* stream) {
+    int64_t T = 0;
+    if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
+    if (!out_d || !minmax_d || !pcm_d || !pcm_h) return fail(GSS_EINVAL, "mask_istft_d2h_pcm16: null pointer");
+    if (chunks < 1) return fail(GSS_EINVAL, "mask_istft_d2h_pcm16: bad chunks");
+    if (int rc = g_cs.init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // a download that still reads this pcm_d (an earlier batch through the same workspace) goes first
+    if (CopyStreams::Tag* t = CopyStreams::find(g_cs.src, pcm_d)) CK(cudaStreamWaitEvent(st, t->ev, 0));
+    const int64_t len = (T - 1) * H;
+    const int64_t per = (B + chunks - 1) / chunks;
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
+        const int64_t nb = (B - b0 < per) ? B - b0 : per;
+        if (int rc = gss_mask_istft(wave_d + b0 * ld, mask_d + b0 * S * T * (N / 2), nb, S, n, ld, N, H,
+                                    out_d + b0 * S * ld_out, ld_out, stream)) return rc;
+        if (int rc = gss_wav16_normalise(out_d + b0 * S * ld_out, nb * S, len, ld_out, minmax_d + 2 * b0 * S,
+                                         pcm_d + b0 * S * len, stream)) return rc;
+        cudaEvent_t ev = g_cs.ev[k % 8];
+        CK(cudaEventRecord(ev, st));
+        CK(cudaStreamWaitEvent(g_cs.d2h, ev, 0));
+        CK(cudaMemcpyAsync(pcm_h + b0 * S * len, pcm_d + b0 * S * len, sizeof(int16_t) * nb * S * len, cudaMemcpyDeviceToHost, g_cs.d2h));
+    }
+    CopyStreams::Tag* ts = nullptr; CopyStreams::Tag* td = nullptr;
+    if (int rc = g_cs.claim(g_cs.src, pcm_d, &ts)) return rc;
+    if (int rc = g_cs.claim(g_cs.dst, pcm_h, &td)) return rc;
+    CK(cudaEventRecord(ts->ev, g_cs.d2h));
+    CK(cudaEventRecord(td->ev, g_cs.d2h));
+    return GSS_OK;
+}
+
 int gss_wait_host(const void* host_ptr) {
     if (!g_cs.ok) return GSS_OK;
     if (!host_ptr) { CK(cudaStreamSynchronize(g_cs.d2h)); return GSS_OK; }     // every pending download

@@ -248,4 +248,10 @@ __global__ void __launch_bounds__(256) apply_mask_bwd_kernel(const float* __rest
     }
 }
 
+// int16 PCM -> float32 (same values, no rescale: the reference feeds raw sample values to SciPy, process.py:97)
+__global__ void __launch_bounds__(256) i16_to_f32_kernel(const int16_t* __restrict__ in, float* __restrict__ out, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (float)__ldg(in + i);
+}
+
 }  // namespace gss

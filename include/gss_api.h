@@ -160,6 +160,20 @@ int gss_mask_istft_d2h_async(const float* wave_d, const float* mask_d, int64_t B
                              int64_t ld_out, int chunks, void* stream);
 int gss_wait_host(const void* host_ptr);
 
+/* The same two stages with int16 PCM on the host link (the sample format of the WAV files main.py:83 reads
+ * and main.py:116 writes): half the bytes each way.  Upload: pcm_h [B,n] -> pcm_d [B,ld] -> features from the
+ * raw sample values (gss_stft_packed_i16, no rescale, like process.py:97) + a float32 copy wave_d [B,ld] that
+ * the synthesis stage reads.  Download: separated waveforms out_d -> per-row shift/scale to [0, 32767]
+ * (main.py:112-116; minmax_d: 2*B*S floats of scratch) -> pcm_d [B*S,(T-1)H] -> pcm_h.  Same ordering rules
+ * as above; gss_wait_host(pcm_h) before reading. */
+int gss_stft_h2d_i16_async(const int16_t* pcm_h, int16_t* pcm_d, float* wave_d, int64_t B, int64_t n,
+                           int64_t ld, int N, int H, int flags, float eps, float* feat_d, int chunks,
+                           void* stream);
+int gss_mask_istft_d2h_pcm16_async(const float* wave_d, const float* mask_d, int64_t B, int S, int64_t n,
+                                   int64_t ld, int N, int H, float* out_d, float* minmax_d,
+                                   int16_t* pcm_d, int16_t* pcm_h, int64_t ld_out, int chunks,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -422,3 +422,31 @@ def test_short_and_ragged_lengths_cover_both_loop_bodies(T, ops, n, H):
     assert R.rel_l2(ops.stft(xd, N, H).cpu().numpy(), ref_f) < REL_L2
     assert R.rel_l2(ops.stft_log(xd, N, H).cpu().numpy(), R.to_log_signal(ref_f)) < REL_L2
     assert R.rel_l2(ops.mask_istft(xd, dev(T, mask), N, H).cpu().numpy(), ref_y) < REL_L2
+
+
+def test_spectral_pipeline_pcm16(T, ops):
+    """int16 PCM at both ends of the host link: features from the raw sample values (process.py:97), outputs
+    min/max-normalised per clip like save_wavfile (main.py:112-116), within 1 LSB of the oracle."""
+    from gan_sass_tf_b200.app.spectral import SpectralPipeline
+    N, H, n, B, S = 512, 128, 6000, 4, 3
+    rng = np.random.default_rng(21)
+    pipe = SpectralPipeline(B, n, S, N, H, chunks=2, depth=2, pcm16=True)
+    pcm = [(speechish(rng, B, n) * 20000).astype(np.int16) for _ in range(3)]
+    masks = [rng.random((B, S, pipe.T, N // 2)).astype(np.float32) for _ in range(3)]
+    got = []
+    for k in range(3):
+        slot = k % 2
+        if k >= 2:
+            got.append(pipe.wait(slot).numpy().copy())
+        f = pipe.analyse(pcm[k], slot=slot, block=False)
+        assert R.rel_l2(f.cpu().numpy(), R.to_log_signal(R.stft_feature_np(pcm[k], N, H))) < REL_L2
+        pipe.synthesise(dev(T, masks[k]), slot=slot, block=False)
+    got.append(pipe.wait(1).numpy().copy())
+    got.append(pipe.wait(0).numpy().copy())
+    order = [0, 1, 2]
+    for k, g in zip(order, got):
+        ref = R.mask_istft_np(pcm[k].astype(np.float32), masks[k], N, H).reshape(B * S, -1)
+        ref_pcm = np.stack([R.wav16_normalise(r.astype(np.float32)) for r in ref])
+        assert g.dtype == np.int16 and g.shape == ref_pcm.shape
+        assert np.max(np.abs(g.astype(np.int32) - ref_pcm.astype(np.int32))) <= 1, f"batch {k}"
+    assert pipe.h2d_bytes == B * n * 2 and pipe.d2h_bytes == B * S * pipe.L * 2
