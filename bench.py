@@ -201,6 +201,15 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # one process per GPU: keep the rank (and the pinned host buffers it allocates) on the CPUs / memory next to
+        # its GPU, otherwise the ranks' host copies all cross the same socket link
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else local))
+        except Exception:
+            pass
+    if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _native.lib()
 

@@ -241,10 +241,12 @@ int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
     k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
     return after_launch("stft_kernel");
 }
-int tune(const char* name, int dflt) {
+#ifdef GSS_TUNE
+int tune(const char* name, int dflt) {      // tuning builds only: kernel variants picked by environment variables
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
 }
+#endif
 template <int N, int HS, bool LOG, typename TIn>
 int launch_stft(gss::StftArgs<TIn> a, cudaStream_t st) {
 #ifdef GSS_TUNE
@@ -317,7 +319,6 @@ int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
     if (int rc = prep(k, smem)) return rc;
     if (int rc = ensure_tables(st)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
-    { static int stg = -1; if (stg < 0) { const char* v = getenv("GSS_STAGGER"); stg = v ? atoi(v) : 0; } a.stagger = stg; }
 #ifdef GSS_TIMING
     static long long* tbuf = nullptr;
     if (!tbuf) cudaMalloc(&tbuf, sizeof(long long) * 8 * 65536);

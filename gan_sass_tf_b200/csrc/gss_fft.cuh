@@ -1,7 +1,7 @@
 // gss_fft.cuh - per-team complex FFT used by every spectral kernel of libgss.
 //
-// Geometry (modelled one-to-one, including the shared-memory layouts, in
-// tools/fft_model.py and checked on the host by tests/test_fft_model.py):
+// Geometry (modelled one-to-one, including the shared-memory layouts and their bank-conflict
+// counts, in tools/fft_model.py and checked on the host by tests/test_fft_model.py):
 //
 //   N = 64*M complex points, M in {4, 8, 16};  a "team" of TPF = N/16 threads owns
 //   one transform, 16 complex points per thread, three passes radix 8 / M / 8.

@@ -236,14 +236,6 @@ struct OlaOut {
     }
 };
 
-// analysis / synthesis windows at this thread's sample positions
-template <class SG>
-__device__ __forceinline__ void make_window(int j, float scale, v2 (&w)[8]) {
-#pragma unroll
-    for (int n0 = 0; n0 < 8; ++n0)
-        w[n0] = make_float2(scale * hann<SG::N>(2 * j + SG::L * n0), scale * hann<SG::N>(2 * j + 1 + SG::L * n0));
-}
-
 struct ChunkPlan { int ppc; int nchunk; };   // pairs per chunk, chunks per row
 
 // ---------------------------------------------------------------------------
@@ -588,7 +580,6 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
 struct SynthArgs {
     const float* wave; const float* mask; float* out;
     long long* timing;              // [items][8] cycle accumulators (GSS_TIMING builds only)
-    int stagger;                    // start skew in cycles between co-resident teams (0 = none)
     int64_t B, n, ld, T, ld_out;
     int S, ngroups;                 // ngroups = ceil(S / ST)
     int npairs, ppc, nchunk;
@@ -657,10 +648,6 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
     const int qs = max(q0 - SG::HALO, 0);
     const bool t0 = j == 0;
 
-    if (p.stagger > 0) {     // de-phase the teams that share an SM sub-partition (they run identical code)
-        const long long tgo = clock64() + (long long)(blockIdx.x & 3) * p.stagger;
-        while (clock64() < tgo) { }
-    }
     TeamCtx<N> ctx;
     team_init_tab<N>(ctx, j, team);
     v2 win[8];                                     // hann / N: analysis scale; synthesis rescaled at the store

@@ -28,8 +28,10 @@ class Geometry:
         self.M = N // 64
         self.TPF = 4 * self.M
         self.L = N // 8
-        # E0: float4 units, [k0][j] -> (re(2j), re(2j+1), im(2j), im(2j+1)); pitch avoids conflicts
+        # E0: two planes (re, im) of 8-byte v2 units, [k0][j] -> (x(2j), x(2j+1)); pitch avoids conflicts
+        # (csrc/gss_fft.cuh: c.e0[k0*P0 + j] and c.e0[E0_PLANE + k0*P0 + j], 64-bit accesses)
         self.P0 = self.TPF + 4
+        self.E0_PLANE_V2 = 8 * self.P0
         # E1: float units, two planes (re, im), [n2][c]
         self.P1 = self.L + 4
         self.E0_FLOATS = 8 * self.P0 * 4
@@ -58,9 +60,9 @@ class Geometry:
     # ---- smem addresses (float index) ----------------------------------
     def e0_addr(self, k0, nprime):
         """float indices (re, im) of element (k0; n')."""
-        a4 = k0 * self.P0 + nprime // 2
+        a2 = k0 * self.P0 + nprime // 2
         e = nprime & 1
-        return 4 * a4 + e, 4 * a4 + 2 + e
+        return 2 * a2 + e, 2 * (self.E0_PLANE_V2 + a2) + e
 
     def e1_addr(self, c, n2):
         f = n2 * self.P1 + c
@@ -277,24 +279,26 @@ def conflict_report(N):
         rep[name] = (a + wf, b + width)
 
     team_off = lambda team: team * (g.E0_FLOATS + g.E1_FLOATS)
-    # E0 write (pass 0): float4 per k0
+    # E0 write (pass 0): one v2 per plane per k0
     for k0 in range(8):
-        acc = []
-        for t in lanes:
-            j, team = team_thread(t) if TPF < 32 else (t, 0)
-            acc.append((t, team_off(team) + 4 * (k0 * g.P0 + j)))
-        add("E0 write (128-bit)", acc, 4)
+        for part in range(2):
+            acc = []
+            for t in lanes:
+                j, team = team_thread(t) if TPF < 32 else (t, 0)
+                acc.append((t, team_off(team) + g.e0_addr(k0, 2 * j)[part]))
+            add("E0 write (64-bit)", acc, 2)
     # E0 read (middle)
     if M in (4, 8):
         ngroups = len(g.mid_butterflies(0))
         for gi in range(ngroups):
             for n1 in range(M):
-                acc = []
-                for t in lanes:
-                    j, team = team_thread(t) if TPF < 32 else (t, 0)
-                    (k0, n2), _ = g.mid_butterflies(j)[gi]
-                    acc.append((t, team_off(team) + g.e0_addr(k0, 8 * n1 + n2)[0]))
-                add("E0 read (128-bit)", acc, 4)
+                for part in range(2):
+                    acc = []
+                    for t in lanes:
+                        j, team = team_thread(t) if TPF < 32 else (t, 0)
+                        (k0, n2), _ = g.mid_butterflies(j)[gi]
+                        acc.append((t, team_off(team) + g.e0_addr(k0, 8 * n1 + n2)[part]))
+                    add("E0 read (64-bit)", acc, 2)
     else:
         for n1 in range(M):
             for part in range(2):
