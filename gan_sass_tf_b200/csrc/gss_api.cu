@@ -53,18 +53,19 @@ int sm_count() {
 // 1 = never the N = 512 register kernels, 2 = gss_generic.cuh only (cross-check paths for the tests)
 std::atomic<int> g_force_generic{0};
 bool fast_n(int N) { return N == 512 && !g_force_generic.load(std::memory_order_relaxed); }   // register-streaming kernels
-// hop in slots for the team kernels, 0 when (N, H) is not covered
+// hop in slots for the team kernels (slot = N/R0 samples: 32, 64, 64, 128, 256), 0 when (N, H) is not covered
 int team_hs(int N, int H) {
     if (g_force_generic.load(std::memory_order_relaxed) >= 2) return 0;
-    int slot = 0;
-    switch (N) { case 256: slot = 64; break; case 512: slot = 128; break; case 1024: slot = 256; break;
-                 case 2048: slot = 512; break; case 4096: slot = 512; break; default: return 0; }
+    int slot = 0, fs = 0;
+    switch (N) { case 256: slot = 32; fs = 8; break; case 512: slot = 64; fs = 8; break; case 1024: slot = 64; fs = 16; break;
+                 case 2048: slot = 128; fs = 16; break; case 4096: slot = 256; fs = 16; break; default: return 0; }
     if (H % slot) return 0;
-    const int hs = H / slot, fs = N / slot;
-    if (hs < 1 || fs % hs || fs / hs < 2) return 0;
+    const int hs = H / slot;
+    if (hs < 1 || fs % hs || fs / hs < 2 || fs / hs > 8) return 0;
     return hs;
 }
-bool supported_n(int N) { return N >= 64 && N <= 4096 && !(N & (N - 1)); }  // the rest: shared-memory FFT
+
+bool supported_n(int N) { return N >= 64 && N <= 4096 && !(N & (N - 1)); }  // sizes without a streaming kernel: per-frame fallback
 
 int check_nh(int N, int H, int* hs) {
     if (N < 16 || (N & (N - 1))) return fail(GSS_EUNSUPPORTED, "FFT_SIZE %d is not a power of two", N);
@@ -177,16 +178,17 @@ int64_t cta_slots(K kernel, int threads, size_t smem) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
     return (int64_t)sm_count() * nb;
 }
-template <int N> size_t team_bytes(int nbuf) { return sizeof(float2) * (size_t)nbuf * (N + N / 16); }
+template <int N> size_t team_bytes(int nbuf) { return sizeof(float2) * (size_t)nbuf * (N + N / gss::team::Plan<N>::R0); }
+template <int N> constexpr int team_threads() { return N / gss::team::Plan<N>::R0; }
 
 template <int N, int HS, typename TIn>
 int team_stft(gss::team::StftArgs<TIn> a, cudaStream_t st) {
     auto k = gss::team::stft_kernel<N, HS, TIn>;
     const size_t smem = team_bytes<N>(2);
     if (int rc = prep(k, smem)) return rc;
-    gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, cta_slots(k, gss::team::Plan<N>::TPT, smem));
+    gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, cta_slots(k, team_threads<N>(), smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
-    k<<<(unsigned)(a.B * a.nchunk), gss::team::Plan<N>::TPT, smem, st>>>(a);
+    k<<<(unsigned)(a.B * a.nchunk), team_threads<N>(), smem, st>>>(a);
     return after_launch("team::stft_kernel");
 }
 template <int N, int HS>
@@ -194,9 +196,9 @@ int team_istft(gss::team::IstftArgs a, cudaStream_t st) {
     auto k = gss::team::istft_kernel<N, HS>;
     const size_t smem = team_bytes<N>(2);
     if (int rc = prep(k, smem)) return rc;
-    gss::ChunkPlan pl = plan_chunks(a.rows, a.npairs, gss::team::TGeo<N, HS>::HALO, cta_slots(k, gss::team::Plan<N>::TPT, smem));
+    gss::ChunkPlan pl = plan_chunks(a.rows, a.npairs, gss::team::TGeo<N, HS>::HALO, cta_slots(k, team_threads<N>(), smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
-    k<<<(unsigned)(a.rows * a.nchunk), gss::team::Plan<N>::TPT, smem, st>>>(a);
+    k<<<(unsigned)(a.rows * a.nchunk), team_threads<N>(), smem, st>>>(a);
     return after_launch("team::istft_kernel");
 }
 template <int N, int HS, int ST>
@@ -205,9 +207,9 @@ int team_synth_st(gss::team::SynthArgs a, cudaStream_t st) {
     const size_t smem = team_bytes<N>(3);
     if (int rc = prep(k, smem)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
-    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::team::TGeo<N, HS>::HALO, cta_slots(k, gss::team::Plan<N>::TPT, smem));
+    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::team::TGeo<N, HS>::HALO, cta_slots(k, team_threads<N>(), smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
-    k<<<(unsigned)(a.B * a.ngroups * a.nchunk), gss::team::Plan<N>::TPT, smem, st>>>(a);
+    k<<<(unsigned)(a.B * a.ngroups * a.nchunk), team_threads<N>(), smem, st>>>(a);
     return after_launch("team::mask_istft_kernel");
 }
 template <int N, int HS>
@@ -218,14 +220,13 @@ int team_synth(gss::team::SynthArgs a, cudaStream_t st) {
     return team_synth_st<N, HS, 3>(a, st);
 }
 // F<N, HS>::run(args...) for the (N, hs) pairs the team kernels cover
-#define GSS_TEAM_DISPATCH(N, hs, CALL)                                                        \
-    do {                                                                                      \
-        if (N == 256 && hs == 1) { CALL(256, 1) } if (N == 256 && hs == 2) { CALL(256, 2) }     \
-        if (N == 512 && hs == 1) { CALL(512, 1) } if (N == 512 && hs == 2) { CALL(512, 2) }     \
-        if (N == 1024 && hs == 1) { CALL(1024, 1) } if (N == 1024 && hs == 2) { CALL(1024, 2) } \
-        if (N == 2048 && hs == 1) { CALL(2048, 1) } if (N == 2048 && hs == 2) { CALL(2048, 2) } \
-        if (N == 4096 && hs == 1) { CALL(4096, 1) } if (N == 4096 && hs == 2) { CALL(4096, 2) } \
-        if (N == 4096 && hs == 4) { CALL(4096, 4) }                                             \
+#define GSS_TEAM_DISPATCH(N, hs, CALL)                                                                              \
+    do {                                                                                                            \
+        if (N == 256 && hs == 1) { CALL(256, 1) } if (N == 256 && hs == 2) { CALL(256, 2) } if (N == 256 && hs == 4) { CALL(256, 4) }       \
+        if (N == 512 && hs == 1) { CALL(512, 1) } if (N == 512 && hs == 2) { CALL(512, 2) } if (N == 512 && hs == 4) { CALL(512, 4) }       \
+        if (N == 1024 && hs == 2) { CALL(1024, 2) } if (N == 1024 && hs == 4) { CALL(1024, 4) } if (N == 1024 && hs == 8) { CALL(1024, 8) } \
+        if (N == 2048 && hs == 2) { CALL(2048, 2) } if (N == 2048 && hs == 4) { CALL(2048, 4) } if (N == 2048 && hs == 8) { CALL(2048, 8) } \
+        if (N == 4096 && hs == 2) { CALL(4096, 2) } if (N == 4096 && hs == 4) { CALL(4096, 4) } if (N == 4096 && hs == 8) { CALL(4096, 8) } \
     } while (0)
 
 // ---- STFT ---------------------------------------------------------------
@@ -279,7 +280,7 @@ int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int 
     if (!fast_n(N)) {
         if (const int ths = team_hs(N, H)) {
             gss::team::StftArgs<TIn> t{};
-            t.wave = wave; t.feat = feat; t.B = B; t.n = n; t.ld = ld; t.T = a.T; t.npairs = a.npairs; t.al_in = a.al_in;
+            t.wave = wave; t.feat = feat; t.B = B; t.n = n; t.ld = ld; t.T = a.T; t.npairs = a.npairs;
             t.log = (flags & GSS_FLAG_LOG) ? 1 : 0; t.eps = eps;
 #define GSS_CALL(NN, HH) return team_stft<NN, HH, TIn>(t, st);
             GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
@@ -501,7 +502,7 @@ int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H, int 
     if (!fast_n(N)) {
         if (const int ths = team_hs(N, H)) {
             gss::team::IstftArgs t{};
-            t.feat = feat; t.out = wave_out; t.rows = R; t.T = T; t.ld_out = ld_out; t.npairs = a.npairs; t.al_out = a.al_out;
+            t.feat = feat; t.out = wave_out; t.rows = R; t.T = T; t.ld_out = ld_out; t.npairs = a.npairs;
             t.exp = (flags & GSS_FLAG_EXP) ? 1 : 0; t.eps = eps;
 #define GSS_CALL(NN, HH) return team_istft<NN, HH>(t, st);
             GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
@@ -540,7 +541,7 @@ int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64
         if (const int ths = team_hs(N, H)) {
             gss::team::SynthArgs t{};
             t.wave = wave; t.mask = mask; t.out = out; t.B = B; t.n = n; t.ld = ld; t.T = a.T; t.ld_out = ld_out; t.S = S;
-            t.npairs = a.npairs; t.al_in = a.al_in; t.al_out = a.al_out;
+            t.npairs = a.npairs;
 #define GSS_CALL(NN, HH) return team_synth<NN, HH>(t, st);
             GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
 #undef GSS_CALL

@@ -124,6 +124,39 @@ __device__ __forceinline__ v2 log_gain2_small(v2 a2, float eps) {
     return vmul(vmul(s, p), make_float2(rsqrtf(e.x), rsqrtf(e.y)));
 }
 
+// scalar forms for kernels that handle one bin per thread at a time (gss_team.cuh): one warp vote picks the
+// polynomial (every lane's a2 <= 1/4, resp. a < 1) or libm; every lane of the warp must call them together
+__device__ __forceinline__ float log_gain_warp(float re, float im, float eps) {
+    const float a2 = fmaf(re, re, im * im);
+    if (__all_sync(0xffffffffu, a2 <= 0.25f)) {
+        float p = fmaf(a2, 3.537580770e-02f, -7.272362134e-02f);
+        p = fmaf(p, a2, 9.832768570e-02f);
+        p = fmaf(p, a2, -1.248603150e-01f);
+        p = fmaf(p, a2, 1.666610216e-01f);
+        p = fmaf(p, a2, -2.499999137e-01f);
+        p = fmaf(p, a2, 4.999999998e-01f);
+        return a2 * p * rsqrtf(a2 + eps);
+    }
+    return 0.5f * log1pf(a2) * rsqrtf(a2 + eps);
+}
+__device__ __forceinline__ float exp_gain_warp(float re, float im, float eps) {
+    const float a2e = fmaf(re, re, fmaf(im, im, eps));
+    if (__all_sync(0xffffffffu, a2e < 1.0f)) {
+        const float a = a2e * rsqrtf(a2e);
+        float p = fmaf(a, 1.0f / 3628800.0f, 1.0f / 362880.0f);
+        p = fmaf(p, a, 1.0f / 40320.0f);
+        p = fmaf(p, a, 1.0f / 5040.0f);
+        p = fmaf(p, a, 1.0f / 720.0f);
+        p = fmaf(p, a, 1.0f / 120.0f);
+        p = fmaf(p, a, 1.0f / 24.0f);
+        p = fmaf(p, a, 1.0f / 6.0f);
+        p = fmaf(p, a, 0.5f);
+        return fmaf(p, a, 1.0f);
+    }
+    const float a = sqrtf(a2e);
+    return expm1f(a) / a;
+}
+
 // per-thread spectrum of a frame pair: bins k = c + L*i, lane x: c = cA, lane y: c = cB
 struct PairSpec {
     v2 ar[4], ai[4];   // frame a: "re" slot feat[k], "im" slot feat[N/2 + k]

@@ -6,15 +6,16 @@
 // one utterance (re = frame 2q, im = frame 2q+1 of one complex N-point transform), the raw-sample
 // ring and the overlap-add accumulators live in registers, every sample is read from global
 // memory once and every output sample written once, no atomics - but the team is a whole CTA of
-// TPT threads and the transform is a Stockham autosort FFT in shared memory: radix-16 / 8 / 4
-// passes, one butterfly per thread per pass, natural order in and out (so the two-for-one split,
-// the mask multiply and the Hermitian pack address bins k and N-k directly, and masks / features
-// are read and written fully coalesced), per-thread twiddles kept in registers as the powers
-// w^1, w^2, w^4, w^8 of the thread's base twiddle and expanded on the fly.
-//
-//   SLOT = 2*TPT samples (thread t owns samples 2t, 2t+1 of every slot); a frame is FS slots,
-//   the hop HS slots.  Buffers are padded by one element per 16 to keep the radix-16 scatter of
-//   the first pass free of bank conflicts.
+// TPT = N/R0 threads and the transform is a three-pass Stockham autosort FFT  N = R0 x RM x R0
+// (radix 8 / 16 outside, 4 / 8 / 16 in the middle), natural order in and out, so the two-for-one
+// split, the mask multiply and the Hermitian pack address bins k and N-k directly and masks /
+// features are read and written fully coalesced.  Thread t owns sample t of every slot of TPT
+// samples - exactly the inputs of its first-pass butterfly (t + r*TPT) and the outputs of its
+// last-pass butterfly - so the first pass of a forward transform reads the windowed samples
+// straight from the register ring and the last pass of an inverse transform feeds the
+// overlap-add accumulators in registers: the data makes two shared-memory round trips per
+// transform instead of four.  Per-thread twiddles live in registers as w^1, w^2, w^4, w^8 and are
+// expanded on the fly; buffers are padded one element per R0 against the first pass's scatter.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -100,31 +101,38 @@ __device__ __forceinline__ void dftR(float2 (&a)[R]) {
 // ---------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------
-template <int N_> struct Plan;      // radices of the passes (product N), team size
-// MINB: resident CTAs per SM the register allocation is held to (128 registers per thread)
-template <> struct Plan<256>  { static constexpr int TPT = 32,  NP = 2, R0 = 16, R1 = 16, R2 = 1,  MINB = 16, MINB_SYNTH = 16; };
-template <> struct Plan<512>  { static constexpr int TPT = 64,  NP = 3, R0 = 8,  R1 = 8,  R2 = 8,  MINB = 8, MINB_SYNTH = 8; };
-template <> struct Plan<1024> { static constexpr int TPT = 128, NP = 3, R0 = 16, R1 = 8,  R2 = 8,  MINB = 4, MINB_SYNTH = 4; };
-template <> struct Plan<2048> { static constexpr int TPT = 256, NP = 3, R0 = 16, R1 = 16, R2 = 8,  MINB = 2, MINB_SYNTH = 2; };
-template <> struct Plan<4096> { static constexpr int TPT = 256, NP = 3, R0 = 16, R1 = 16, R2 = 16, MINB = 2, MINB_SYNTH = 1; };
+// N = R0 * RM * R0; TPT = N / R0 threads; MINB*: resident CTAs per SM the register allocation is held to, per kernel
+// (chosen so that nothing spills: the radix-16 butterflies with their expanded twiddles are register-hungry, and a
+// spilling synthesis kernel at 12 warps/SM measured 15 % slower than a clean one at 8)
+template <int N_> struct Plan;
+template <> struct Plan<256>  { static constexpr int R0 = 8,  RM = 4,  MINB = 16, MINB_ISTFT = 16, MINB_SYNTH = 16; };
+template <> struct Plan<512>  { static constexpr int R0 = 8,  RM = 8,  MINB = 8,  MINB_ISTFT = 8,  MINB_SYNTH = 8; };
+template <> struct Plan<1024> { static constexpr int R0 = 16, RM = 4,  MINB = 8,  MINB_ISTFT = 6,  MINB_SYNTH = 4; };
+template <> struct Plan<2048> { static constexpr int R0 = 16, RM = 8,  MINB = 4,  MINB_ISTFT = 3,  MINB_SYNTH = 2; };
+template <> struct Plan<4096> { static constexpr int R0 = 16, RM = 16, MINB = 2,  MINB_ISTFT = 1,  MINB_SYNTH = 1; };
 
 template <int N_, int HS_>
 struct TGeo {
     typedef Plan<N_> P;
-    static constexpr int N = N_, HS = HS_, TPT = P::TPT;
-    static constexpr int SLOT = 2 * TPT;
-    static constexpr int FS = N / SLOT;            // slots per frame (4, or 8 at N = 4096)
+    static constexpr int N = N_, HS = HS_, R0 = P::R0, RM = P::RM;
+    static constexpr int TPT = N / R0;             // threads per team = samples per slot
+    static constexpr int SLOT = TPT;
+    static constexpr int FS = R0;                  // slots per frame
     static constexpr int H = HS * SLOT;
     static constexpr int R = FS / HS;              // frames covering one sample
     static constexpr int RS = FS + HS;             // slots spanned by a frame pair
     static constexpr int ADV = 2 * HS;
     static constexpr int KEEP = RS - ADV;
-    static constexpr int HALO = R / 2;
+    static constexpr int HALO = R / 2;             // pairs to recompute before an owned run: ceil((R-1)/2)
     static constexpr bool CONST_NORM = (R >= 4);
-    static constexpr int PADN = N + N / 16;        // padded complex elements per buffer
+    static constexpr int PADN = N + N / R0;        // padded complex elements per buffer
+    static constexpr int NMID = N / RM;            // middle-pass butterflies
+    static constexpr int BPT = (NMID + TPT - 1) / TPT;   // ... per thread (1, 2 or 4)
+    static_assert(N == R0 * RM * R0, "plan must factor N");
     static_assert(FS % HS == 0 && R >= 2, "hop must divide the frame into >= 2 parts");
+    static_assert(R0 % RM == 0 || RM % R0 == 0, "middle butterflies of one thread must share their twiddles");
 };
-__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
+template <int R0> __device__ __forceinline__ int pad(int i) { return i + i / R0; }
 
 // read-only global load that stays where it is written: the compiler is free to sink a plain __ldg past
 // the CTA barriers down to its use (saving registers, exposing the whole DRAM latency); prefetches must not move
@@ -134,87 +142,126 @@ __device__ __forceinline__ float ldg_here(const float* p) {
     return v;
 }
 
-// base twiddles of one pass for this thread: W_(NS*R)^(k * 2^i), k = j mod NS
+// powers w^1 .. w^(R-1) from the stored w^1, w^2, w^4, w^8
 struct PassTw { float2 w[4]; };
-template <int R, int NS>
-__device__ __forceinline__ void init_pass_tw(PassTw& p, int j) {
-    const int k = j & (NS - 1);
+template <int R>
+__device__ __forceinline__ void expand(const PassTw& tw, float2 (&w)[R]) {
+    w[1] = tw.w[0];
+    if (R > 2) { w[2] = tw.w[1]; w[3] = cmul2(w[1], w[2]); }
+    if (R > 4) { w[4] = tw.w[2]; w[5] = cmul2(w[1], w[4]); w[6] = cmul2(w[2], w[4]); w[7] = cmul2(w[3], w[4]); }
+    if (R > 8) {
+        w[8] = tw.w[3];
+#pragma unroll
+        for (int r = 9; r < R; ++r) w[r] = cmul2(w[r - 8], w[8]);
+    }
+}
+// W_period^(k * 2^i), i = 0..3
+__device__ __forceinline__ void init_pass_tw(PassTw& p, int k, int period) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float s, c;
-        sincospif(-2.0f * (float)(k << i) / (float)(NS * R), &s, &c);
+        sincospif(-2.0f * (float)(k << i) / (float)period, &s, &c);
         p.w[i] = make_float2(c, s);
     }
 }
+template <class G>
+struct TeamTw { PassTw mid, last; };
+template <class G>
+__device__ __forceinline__ void init_tw(TeamTw<G>& t, int j) {
+    init_pass_tw(t.mid, j % G::R0, G::R0 * G::RM);       // middle pass: NS = R0, k = j mod R0 (same for j + TPT)
+    init_pass_tw(t.last, j, G::N);                       // last pass:   NS = N/R0 = TPT, k = j
+}
 
-// one Stockham pass: thread j < N/R, k = j mod NS:
-//   v[r] = in[j + r N/R] * w^r ;  V = DFT_R(v) ;  out[(j - k) R + k + r NS] = V[r]
-template <int N, int R, int NS, bool INV>
-__device__ __forceinline__ void pass(const float2* __restrict__ in, float2* __restrict__ out, const PassTw& tw, int j) {
-    if (j < N / R) {
-        float2 v[R];
+// Stockham passes (DIT):  v[r] = in[j + r N/R] * w^r ;  V = DFT_R(v) ;  out[(j - k) R + k + r NS] = V[r],  k = j mod NS
+// first pass (NS = 1): inputs given in registers (the windowed frame pair, or loaded by the caller)
+template <class G, bool INV>
+__device__ __forceinline__ void first_pass(float2 (&v)[G::R0], float2* __restrict__ out, int j) {
+    dftR<G::R0, INV>(v);
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = in[pad(j + r * (N / R))];
-        if (NS > 1) {
-            float2 w[R];
-            w[1] = tw.w[0];
-            if (R > 2) { w[2] = tw.w[1]; w[3] = cmul2(w[1], w[2]); }
-            if (R > 4) { w[4] = tw.w[2]; w[5] = cmul2(w[1], w[4]); w[6] = cmul2(w[2], w[4]); w[7] = cmul2(w[3], w[4]); }
-            if (R > 8) {
-                w[8] = tw.w[3];
+    for (int r = 0; r < G::R0; ++r) out[pad<G::R0>(j * G::R0 + r)] = v[r];
+}
+template <class G>
+__device__ __forceinline__ void load_first(const float2* __restrict__ in, float2 (&v)[G::R0], int j) {
 #pragma unroll
-                for (int r = 9; r < R; ++r) w[r] = cmul2(w[r - 8], w[8]);
-            }
+    for (int r = 0; r < G::R0; ++r) v[r] = in[pad<G::R0>(j + r * G::TPT)];
+}
+// middle pass (NS = R0): NMID butterflies, BPT per thread
+template <class G, bool INV>
+__device__ __forceinline__ void mid_pass(const float2* __restrict__ in, float2* __restrict__ out, const PassTw& tw, int j) {
+    constexpr int R = G::RM;
+    float2 w[R];
+    expand<R>(tw, w);
+    const int k = j % G::R0;
+#pragma unroll
+    for (int b = 0; b < G::BPT; ++b) {
+        const int jb = j + b * G::TPT;
+        if (jb < G::NMID) {
+            float2 v[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = in[pad<G::R0>(jb + r * G::NMID)];
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = twmul<INV>(v[r], w[r]);
-        }
-        dftR<R, INV>(v);
-        const int k = j & (NS - 1);
-        const int o = (j - k) * R + k;
+            dftR<R, INV>(v);
+            const int o = (jb - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) out[pad(o + r * NS)] = v[r];
+            for (int r = 0; r < R; ++r) out[pad<G::R0>(o + r * G::R0)] = v[r];
+        }
     }
 }
-
-template <int N>
-struct TeamTw { PassTw p1, p2; };
-
-template <int N>
-__device__ __forceinline__ void init_tw(TeamTw<N>& t, int j) {
-    typedef Plan<N> P;
-    init_pass_tw<P::R1, P::R0>(t.p1, j);
-    if constexpr (P::NP > 2) init_pass_tw<P::R2, P::R0 * P::R1>(t.p2, j);
+// last pass (NS = TPT, k = j): outputs are elements j + r*TPT - left in registers
+template <class G, bool INV>
+__device__ __forceinline__ void last_pass(const float2* __restrict__ in, float2 (&v)[G::R0], const PassTw& tw, int j) {
+    constexpr int R = G::R0;
+    float2 w[R];
+    expand<R>(tw, w);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = in[pad<R>(j + r * G::TPT)];
+#pragma unroll
+    for (int r = 1; r < R; ++r) v[r] = twmul<INV>(v[r], w[r]);
+    dftR<R, INV>(v);
+}
+template <class G>
+__device__ __forceinline__ void store_natural(const float2 (&v)[G::R0], float2* __restrict__ out, int j) {
+#pragma unroll
+    for (int r = 0; r < G::R0; ++r) out[pad<G::R0>(j + r * G::TPT)] = v[r];
 }
 
-// N-point complex FFT of b0 (natural order); b1 is scratch.  Returns the buffer holding the result
-// (b1 after an odd number of passes, b0 after an even number).  Ends with a CTA barrier.
-template <int N, bool INV>
-__device__ __forceinline__ float2* fft(float2* b0, float2* b1, const TeamTw<N>& tw, int j) {
-    typedef Plan<N> P;
-    PassTw none;
-    pass<N, P::R0, 1, INV>(b0, b1, none, j);
+// forward transform of the frame pair held in the ring: result (natural order) in A; B is scratch
+template <class G>
+__device__ __forceinline__ void forward_from_ring(const float (&ring)[G::RS], const float (&win)[G::FS], float2* A, float2* B,
+                                                  const TeamTw<G>& tw, int j) {
+    float2 v[G::R0];
+#pragma unroll
+    for (int r = 0; r < G::R0; ++r) v[r] = make_float2(ring[r] * win[r], ring[G::HS + r] * win[r]);
+    first_pass<G, false>(v, A, j);
     __syncthreads();
-    pass<N, P::R1, P::R0, INV>(b1, b0, tw.p1, j);
+    mid_pass<G, false>(A, B, tw.mid, j);
     __syncthreads();
-    if constexpr (P::NP > 2) {
-        pass<N, P::R2, P::R0 * P::R1, INV>(b0, b1, tw.p2, j);
-        __syncthreads();
-        return b1;
-    } else {
-        return b0;
-    }
+    last_pass<G, false>(B, v, tw.last, j);
+    store_natural<G>(v, A, j);
+    __syncthreads();
+}
+// inverse transform of Y (natural order, in Y; W is scratch): element j + r*TPT = (frame a, frame b) sample in v[r]
+template <class G>
+__device__ __forceinline__ void inverse_to_regs(float2* Y, float2* W, float2 (&v)[G::R0], const TeamTw<G>& tw, int j) {
+    load_first<G>(Y, v, j);
+    first_pass<G, true>(v, W, j);
+    __syncthreads();
+    mid_pass<G, true>(W, Y, tw.mid, j);
+    __syncthreads();
+    last_pass<G, true>(Y, v, tw.last, j);
 }
 
 // ---------------------------------------------------------------------------
-// sample access and overlap-add output (thread t owns samples 2t, 2t+1 of every slot)
+// sample access and overlap-add output (thread t owns sample t of every slot)
 // ---------------------------------------------------------------------------
-template <int SLOT, int FS, int CNT, typename TIn>
-__device__ __forceinline__ void load_slots(const TIn* row, int64_t n, int64_t sl, int t, bool al, v2* dst) {
-    const bool inside = sl >= FS / 2 && (sl + CNT - FS / 2) * SLOT <= n;
+template <class G, int CNT, typename TIn>
+__device__ __forceinline__ void load_slots(const TIn* row, int64_t n, int64_t sl, int t, float* dst) {
+    const bool inside = sl >= G::FS / 2 && (sl + CNT - G::FS / 2) * G::SLOT <= n;
 #pragma unroll
     for (int i = 0; i < CNT; ++i) {
-        const int64_t p = (sl + i - FS / 2) * SLOT + 2 * t;
-        dst[i] = inside ? load_pair_fast(row, p, al) : load_pair_edge(row, n, p);
+        const int64_t p = (sl + i - G::FS / 2) * G::SLOT + t;
+        dst[i] = (inside || (p >= 0 && p < n)) ? (float)__ldg(row + p) : 0.f;
     }
 }
 
@@ -222,73 +269,66 @@ template <class G>
 struct Ola {
     int64_t T;
     int t;
-    bool al;
     float oscale;
-    v2 invn[G::HS];
+    float invn[G::HS];
     static constexpr float kScale = G::CONST_NORM ? 0.5f / (0.375f * G::R) : 0.5f;
 
-    __device__ __forceinline__ void init(int64_t T_, int t_, bool al_, float win_gain) {
-        T = T_; t = t_; al = al_;
+    __device__ __forceinline__ void init(int64_t T_, int t_, float win_gain) {
+        T = T_; t = t_;
         oscale = kScale * win_gain;
         if (!G::CONST_NORM) {
 #pragma unroll
             for (int m = 0; m < G::HS; ++m) {
-                float s0 = 0.f, s1 = 0.f;
-                for (int r = 0; r < G::R; ++r) {
-                    float w0 = hann<G::N>(m * G::SLOT + 2 * t + r * G::H);
-                    float w1 = hann<G::N>(m * G::SLOT + 2 * t + 1 + r * G::H);
-                    s0 += w0 * w0; s1 += w1 * w1;
-                }
-                invn[m] = make_float2(oscale / s0, oscale / s1);
+                float s0 = 0.f;
+                for (int r = 0; r < G::R; ++r) { float w0 = hann<G::N>(m * G::SLOT + t + r * G::H); s0 += w0 * w0; }
+                invn[m] = oscale / s0;
             }
         }
     }
-    __device__ __noinline__ float norm_at(int64_t sl, int e) const {
+    // actual sum_f w^2 over the frames that exist (edges of the signal)
+    __device__ __noinline__ float norm_at(int64_t sl) const {
         int64_t tlo = sl - (G::FS - 1); tlo = tlo <= 0 ? 0 : (tlo + G::HS - 1) / G::HS;
         int64_t thi = sl / G::HS; if (thi > T - 1) thi = T - 1;
         float s = 0.f;
         for (int64_t f = tlo; f <= thi; ++f) {
-            int i = (int)((sl - f * G::HS) * G::SLOT) + 2 * t + e;
-            float w = hann<G::N>(i);
+            float w = hann<G::N>((int)((sl - f * G::HS) * G::SLOT) + t);
             s += w * w;
         }
-        return s > 1e-10f ? s : 1.0f;
+        return s > 1e-10f ? s : 1.0f;     // scipy.signal.istft: where(norm > 1e-10, norm, 1)
     }
-    __device__ __forceinline__ void write(float* row, int64_t sl, int m, v2 v) const {
-        v = vmul(v, G::CONST_NORM ? vset(oscale) : invn[m]);
+    __device__ __forceinline__ void write(float* row, int64_t sl, int m, float v) const {
+        v *= G::CONST_NORM ? oscale : invn[m];
         if (sl < G::FS / 2 || sl >= G::FS / 2 + (T - 1) * G::HS) return;
-        if (G::CONST_NORM && (sl <= G::FS - 1 - G::HS || sl >= T * G::HS)) {
-            const float c = 0.375f * G::R;
-            v.x *= c / norm_at(sl, 0); v.y *= c / norm_at(sl, 1);
-        }
-        float* p = row + (sl - G::FS / 2) * G::SLOT + 2 * t;
-        if (al) *reinterpret_cast<float2*>(p) = v; else { p[0] = v.x; p[1] = v.y; }
+        if (G::CONST_NORM && (sl <= G::FS - 1 - G::HS || sl >= T * G::HS)) v *= (0.375f * G::R) / norm_at(sl);
+        row[(sl - G::FS / 2) * G::SLOT + t] = v;
     }
 };
 
 template <class G>
-__device__ __forceinline__ void make_window(int t, float scale, v2 (&w)[G::FS]) {
+__device__ __forceinline__ void make_window(int t, float scale, float (&w)[G::FS]) {
 #pragma unroll
-    for (int i = 0; i < G::FS; ++i)
-        w[i] = make_float2(scale * hann<G::N>(2 * t + G::SLOT * i), scale * hann<G::N>(2 * t + 1 + G::SLOT * i));
-}
-
-// windowed frame pair -> z[n] = (frame a, frame b) in natural order
-template <class G>
-__device__ __forceinline__ void stage_pair(const v2 (&ring)[G::RS], const v2 (&win)[G::FS], float2* z, int t) {
-#pragma unroll
-    for (int i = 0; i < G::FS; ++i) {
-        const v2 a = vmul(ring[i], win[i]), b = vmul(ring[G::HS + i], win[i]);
-        const int p = pad(2 * t + G::SLOT * i);          // 2t is even: 2t and 2t+1 share a 16-group
-        z[p] = make_float2(a.x, b.x);
-        z[p + 1] = make_float2(a.y, b.y);
-    }
+    for (int i = 0; i < G::FS; ++i) w[i] = scale * hann<G::N>(t + G::SLOT * i);
 }
 
 // two-for-one: spectra of frames a and b at bin k from Z[k], Z[N-k] (the window carries the 1/2)
 __device__ __forceinline__ void split_bin(float2 zk, float2 zn, float2& A, float2& B) {
     A = make_float2(zk.x + zn.x, zk.y - zn.y);            // Z[k] + conj Z[N-k]
     B = make_float2(zk.y + zn.y, zn.x - zk.x);            // (Z[k] - conj Z[N-k]) / i
+}
+// spectra Ya, Yb of two real frames at bin k (k in [0, N/2]) -> Y[k], Y[N-k] of the complex transform
+template <int R0>
+__device__ __forceinline__ void pack_bin(float2 Ya, float2 Yb, float2* Y, int k, int N) {
+    Y[pad<R0>(k)] = make_float2(Ya.x - Yb.y, Ya.y + Yb.x);                       // Ya + i Yb
+    Y[pad<R0>((N - k) & (N - 1))] = make_float2(Ya.x + Yb.y, Yb.x - Ya.y);       // conj(Ya) + i conj(Yb)
+}
+// inverse-transform outputs of this thread -> overlap-add accumulators
+template <class G>
+__device__ __forceinline__ void ola_accumulate(const float2 (&v)[G::R0], const float (&win)[G::FS], float (&cur)[G::RS]) {
+#pragma unroll
+    for (int r = 0; r < G::FS; ++r) {
+        cur[r] = fmaf(v[r].x, win[r], cur[r]);
+        cur[G::HS + r] = fmaf(v[r].y, win[r], cur[G::HS + r]);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -299,58 +339,56 @@ struct StftArgs {
     const TIn* wave; float* feat;
     int64_t B, n, ld, T;
     int npairs, ppc, nchunk;
-    int al_in; int log; float eps;
+    int log; float eps;
 };
 
 template <int N, int HS, typename TIn>
-__global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB) stft_kernel(const StftArgs<TIn> p) {
+__global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB) stft_kernel(const StftArgs<TIn> p) {
     typedef TGeo<N, HS> G;
+    constexpr int R0 = G::R0;
     extern __shared__ float4 smem4[];
-    float2* b0 = reinterpret_cast<float2*>(smem4);
-    float2* b1 = b0 + G::PADN;
+    float2* A = reinterpret_cast<float2*>(smem4);
+    float2* Bf = A + G::PADN;
     const int t = threadIdx.x;
     const int64_t item = blockIdx.x;
     const int64_t b = item / p.nchunk;
     const int c = (int)(item - b * p.nchunk);
     const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
 
-    TeamTw<N> tw; init_tw<N>(tw, t);
-    v2 win[G::FS];
-    make_window<G>(t, 1.0f / (float)N, win);
+    TeamTw<G> tw; init_tw<G>(tw, t);
+    float win[G::FS];
+    make_window<G>(t, 1.0f / (float)N, win);       // 1/sum(w) = 2/N, and the 1/2 of the two-for-one split
     const TIn* row = p.wave + b * p.ld;
-    const bool al = p.al_in != 0;
     int64_t base = (int64_t)2 * q0 * HS;
-    v2 ring[G::RS];
-    load_slots<G::SLOT, G::FS, G::RS>(row, p.n, base, t, al, ring);
+    float ring[G::RS];
+    load_slots<G, G::RS>(row, p.n, base, t, ring);
 
     for (int q = q0; q < q1; ++q) {
-        stage_pair<G>(ring, win, b0, t);
+        forward_from_ring<G>(ring, win, A, Bf, tw, t);
 #pragma unroll
         for (int i = 0; i < G::KEEP; ++i) ring[i] = ring[i + G::ADV];
-        if (q + 1 < q1) load_slots<G::SLOT, G::FS, G::ADV>(row, p.n, base + G::RS, t, al, &ring[G::KEEP]);
-        __syncthreads();
-        const float2* Z = fft<N, false>(b0, b1, tw, t);
+        if (q + 1 < q1) load_slots<G, G::ADV>(row, p.n, base + G::RS, t, &ring[G::KEEP]);
         const int64_t ta = 2 * (int64_t)q;
         float* fa = p.feat + (b * p.T + ta) * N;
         const bool hb = ta + 1 < p.T;
         for (int k = t; k < N / 2; k += G::TPT) {
-            float2 A, B;
-            split_bin(Z[pad(k)], Z[pad((N - k) & (N - 1))], A, B);
+            float2 Sa, Sb;
+            split_bin(A[pad<R0>(k)], A[pad<R0>((N - k) & (N - 1))], Sa, Sb);
             if (k == 0) {               // slot 0 carries (DC, Nyquist) (app/utils.py:22-26)
                 float2 An, Bn;
-                const float2 zh = Z[pad(N / 2)];
+                const float2 zh = A[pad<R0>(N / 2)];
                 split_bin(zh, zh, An, Bn);
-                A.y = An.x; B.y = Bn.x;
+                Sa.y = An.x; Sb.y = Bn.x;
             }
             if (p.log) {
-                float g = log_gain(A.x, A.y, p.eps); A.x *= g; A.y *= g;
-                g = log_gain(B.x, B.y, p.eps); B.x *= g; B.y *= g;
+                float g = log_gain_warp(Sa.x, Sa.y, p.eps); Sa.x *= g; Sa.y *= g;
+                g = log_gain_warp(Sb.x, Sb.y, p.eps); Sb.x *= g; Sb.y *= g;
             }
-            fa[k] = A.x; fa[N / 2 + k] = A.y;
-            if (hb) { fa[N + k] = B.x; fa[N + N / 2 + k] = B.y; }
+            fa[k] = Sa.x; fa[N / 2 + k] = Sa.y;
+            if (hb) { fa[N + k] = Sb.x; fa[N + N / 2 + k] = Sb.y; }
         }
         base += G::ADV;
-        __syncthreads();
+        __syncthreads();                            // A is rewritten by the next pair's first pass
     }
 }
 
@@ -358,32 +396,16 @@ struct IstftArgs {
     const float* feat; float* out;
     int64_t rows, T, ld_out;
     int npairs, ppc, nchunk;
-    int al_out; int exp; float eps;
+    int exp; float eps;
 };
 
-// spectra Ya, Yb of two real frames at bin k (k in [0, N/2]) -> Y[k], Y[N-k] of the complex transform
-__device__ __forceinline__ void pack_bin(float2 Ya, float2 Yb, float2* Y, int k, int N) {
-    Y[pad(k)] = make_float2(Ya.x - Yb.y, Ya.y + Yb.x);                       // Ya + i Yb
-    Y[pad((N - k) & (N - 1))] = make_float2(Ya.x + Yb.y, Yb.x - Ya.y);       // conj(Ya) + i conj(Yb)
-}
-
-template <class G>
-__device__ __forceinline__ void ola_accumulate(const float2* z, const v2 (&win)[G::FS], v2 (&cur)[G::RS], int t) {
-#pragma unroll
-    for (int i = 0; i < G::FS; ++i) {
-        const int p = pad(2 * t + G::SLOT * i);
-        const float2 z0 = z[p], z1 = z[p + 1];
-        cur[i] = vfma(make_float2(z0.x, z1.x), win[i], cur[i]);
-        cur[G::HS + i] = vfma(make_float2(z0.y, z1.y), win[i], cur[G::HS + i]);
-    }
-}
-
 template <int N, int HS>
-__global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB) istft_kernel(const IstftArgs p) {
+__global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_ISTFT) istft_kernel(const IstftArgs p) {
     typedef TGeo<N, HS> G;
+    constexpr int R0 = G::R0;
     extern __shared__ float4 smem4[];
-    float2* b0 = reinterpret_cast<float2*>(smem4);
-    float2* b1 = b0 + G::PADN;
+    float2* A = reinterpret_cast<float2*>(smem4);
+    float2* Bf = A + G::PADN;
     const int t = threadIdx.x;
     const int64_t item = blockIdx.x;
     const int64_t r = item / p.nchunk;
@@ -391,16 +413,17 @@ __global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB) istft_kernel(cons
     const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
     const int qs = max(q0 - G::HALO, 0);
 
-    TeamTw<N> tw; init_tw<N>(tw, t);
-    v2 win[G::FS];
+    TeamTw<G> tw; init_tw<G>(tw, t);
+    float win[G::FS];
+    // frame = sum(w) * irfft = (N/2)(1/N) * raw inverse: the 1/2 and 1/sum(w^2) are applied at the store
     make_window<G>(t, 1.0f, win);
     Ola<G> o;
-    o.init(p.T, t, p.al_out != 0, 1.0f);
+    o.init(p.T, t, 1.0f);
     float* orow = p.out + r * p.ld_out;
     const float* frow = p.feat + r * p.T * N;
-    v2 acc[G::KEEP];
+    float acc[G::KEEP];
 #pragma unroll
-    for (int i = 0; i < G::KEEP; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < G::KEEP; ++i) acc[i] = 0.f;
     int64_t base = (int64_t)2 * qs * HS;
 
     // packed features of this thread's bins k = t + i*TPT (slot 0 also feeds bin N/2), fetched one pair ahead
@@ -424,21 +447,22 @@ __global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB) istft_kernel(cons
             const int k = t + i * G::TPT;
             float2 Ya = fya[i], Yb = fyb[i];
             if (p.exp) {          // to_exp pairs slot 0 = (DC, Nyquist) like every other bin pair (ops.py:247)
-                float g = exp_gain(Ya.x, Ya.y, p.eps); Ya.x *= g; Ya.y *= g;
-                g = exp_gain(Yb.x, Yb.y, p.eps); Yb.x *= g; Yb.y *= g;
+                float g = exp_gain_warp(Ya.x, Ya.y, p.eps); Ya.x *= g; Ya.y *= g;
+                g = exp_gain_warp(Yb.x, Yb.y, p.eps); Yb.x *= g; Yb.y *= g;
             }
             if (k == 0) {         // bin 0 -> (f[0], 0), bin N/2 -> (f[N/2], 0)
-                pack_bin(make_float2(Ya.y, 0.f), make_float2(Yb.y, 0.f), b0, N / 2, N);
+                pack_bin<R0>(make_float2(Ya.y, 0.f), make_float2(Yb.y, 0.f), A, N / 2, N);
                 Ya.y = 0.f; Yb.y = 0.f;
             }
-            pack_bin(Ya, Yb, b0, k, N);
+            pack_bin<R0>(Ya, Yb, A, k, N);
         }
         __syncthreads();
-        const float2* z = fft<N, true>(b0, b1, tw, t);
-        v2 cur[G::RS];
+        float2 v[R0];
+        inverse_to_regs<G>(A, Bf, v, tw, t);
+        float cur[G::RS];
 #pragma unroll
-        for (int i = 0; i < G::RS; ++i) cur[i] = i < G::KEEP ? acc[i] : make_float2(0.f, 0.f);
-        ola_accumulate<G>(z, win, cur, t);
+        for (int i = 0; i < G::RS; ++i) cur[i] = i < G::KEEP ? acc[i] : 0.f;
+        ola_accumulate<G>(v, win, cur);
         if (q >= q0) {
 #pragma unroll
             for (int i = 0; i < G::ADV; ++i) o.write(orow, base + i, i % HS, cur[i]);
@@ -448,7 +472,7 @@ __global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB) istft_kernel(cons
 #pragma unroll
         for (int i = 0; i < KI; ++i) { fya[i] = nya[i]; fyb[i] = nyb[i]; }      // the next pair's features have had a whole transform to arrive
         base += G::ADV;
-        __syncthreads();
+        __syncthreads();                            // A (read by the last pass) is rewritten by the next pair's pack
     }
     if (c == p.nchunk - 1) {
 #pragma unroll
@@ -461,17 +485,16 @@ struct SynthArgs {
     int64_t B, n, ld, T, ld_out;
     int S, ngroups;
     int npairs, ppc, nchunk;
-    int al_in, al_out;
 };
 
 template <int N, int HS, int ST>
-__global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB_SYNTH) mask_istft_kernel(const SynthArgs p) {
+__global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_SYNTH) mask_istft_kernel(const SynthArgs p) {
     typedef TGeo<N, HS> G;
-    constexpr int NH = N / 2;
+    constexpr int NH = N / 2, R0 = G::R0;
     extern __shared__ float4 smem4[];
-    float2* b0 = reinterpret_cast<float2*>(smem4);
-    float2* b1 = b0 + G::PADN;
-    float2* b2 = b1 + G::PADN;
+    float2* X = reinterpret_cast<float2*>(smem4);      // mixture spectrum of the pair, kept for every source
+    float2* Y = X + G::PADN;
+    float2* W = Y + G::PADN;
     const int t = threadIdx.x;
     const int64_t item = blockIdx.x;
     const int64_t per_b = (int64_t)p.ngroups * p.nchunk;
@@ -483,36 +506,30 @@ __global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB_SYNTH) mask_istft_
     const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
     const int qs = max(q0 - G::HALO, 0);
 
-    TeamTw<N> tw; init_tw<N>(tw, t);
-    v2 win[G::FS];
-    make_window<G>(t, 1.0f / (float)N, win);
+    TeamTw<G> tw; init_tw<G>(tw, t);
+    float win[G::FS];
+    make_window<G>(t, 1.0f / (float)N, win);       // hann / N: analysis scale; synthesis rescaled at the store
     Ola<G> o;
-    o.init(p.T, t, p.al_out != 0, (float)N);
+    o.init(p.T, t, (float)N);
     float* orow0 = p.out + (b * p.S + s0) * p.ld_out;
     const float* mrow0 = p.mask + ((b * p.S + s0) * p.T) * NH;
     const int64_t msrc = p.T * NH;
     const float* row = p.wave + b * p.ld;
-    const bool al = p.al_in != 0;
 
-    v2 acc[ST][G::KEEP];
+    float acc[ST][G::KEEP];
 #pragma unroll
     for (int s = 0; s < ST; ++s)
 #pragma unroll
-        for (int i = 0; i < G::KEEP; ++i) acc[s][i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < G::KEEP; ++i) acc[s][i] = 0.f;
     int64_t base = (int64_t)2 * qs * HS;
-    v2 ring[G::RS];
-    load_slots<G::SLOT, G::FS, G::RS>(row, p.n, base, t, al, ring);
+    float ring[G::RS];
+    load_slots<G, G::RS>(row, p.n, base, t, ring);
 
     for (int q = qs; q < q1; ++q) {
-        stage_pair<G>(ring, win, b0, t);
+        forward_from_ring<G>(ring, win, X, Y, tw, t);
 #pragma unroll
         for (int i = 0; i < G::KEEP; ++i) ring[i] = ring[i + G::ADV];
-        if (q + 1 < q1) load_slots<G::SLOT, G::FS, G::ADV>(row, p.n, base + G::RS, t, al, &ring[G::KEEP]);
-        __syncthreads();
-        // mixture spectrum stays in X for every source; Y / W are the two buffers the inverse uses
-        float2* X = fft<N, false>(b0, b1, tw, t);
-        float2* Y = (X == b0) ? b1 : b0;
-        float2* W = b2;
+        if (q + 1 < q1) load_slots<G, G::ADV>(row, p.n, base + G::RS, t, &ring[G::KEEP]);
         const int64_t ta = 2 * (int64_t)q;
         const bool hb = ta + 1 < p.T;
         const bool own = q >= q0;
@@ -532,21 +549,22 @@ __global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB_SYNTH) mask_istft_
 #pragma unroll
                 for (int i = 0; i < KI; ++i) {
                     const int k = t + i * G::TPT;
-                    float2 A, B;
-                    split_bin(X[pad(k)], X[pad((N - k) & (N - 1))], A, B);
-                    pack_bin(make_float2(A.x * ga[i], A.y * ga[i]), make_float2(B.x * gb[i], B.y * gb[i]), Y, k, N);
+                    float2 Sa, Sb;
+                    split_bin(X[pad<R0>(k)], X[pad<R0>((N - k) & (N - 1))], Sa, Sb);
+                    pack_bin<R0>(make_float2(Sa.x * ga[i], Sa.y * ga[i]), make_float2(Sb.x * gb[i], Sb.y * gb[i]), Y, k, N);
                 }
                 if (t == 0) {                                      // Nyquist: shares gain 0 with DC (ops.py:234-237)
-                    float2 A, B;
-                    split_bin(X[pad(NH)], X[pad(NH)], A, B);
-                    pack_bin(make_float2(A.x * ga[0], A.y * ga[0]), make_float2(B.x * gb[0], B.y * gb[0]), Y, NH, N);
+                    float2 Sa, Sb;
+                    split_bin(X[pad<R0>(NH)], X[pad<R0>(NH)], Sa, Sb);
+                    pack_bin<R0>(make_float2(Sa.x * ga[0], Sa.y * ga[0]), make_float2(Sb.x * gb[0], Sb.y * gb[0]), Y, NH, N);
                 }
                 __syncthreads();
-                const float2* z = fft<N, true>(Y, W, tw, t);
-                v2 cur[G::RS];
+                float2 v[R0];
+                inverse_to_regs<G>(Y, W, v, tw, t);
+                float cur[G::RS];
 #pragma unroll
-                for (int i = 0; i < G::RS; ++i) cur[i] = i < G::KEEP ? acc[s][i] : make_float2(0.f, 0.f);
-                ola_accumulate<G>(z, win, cur, t);
+                for (int i = 0; i < G::RS; ++i) cur[i] = i < G::KEEP ? acc[s][i] : 0.f;
+                ola_accumulate<G>(v, win, cur);
                 if (own) {
                     float* orow = orow0 + s * p.ld_out;
 #pragma unroll
@@ -556,7 +574,7 @@ __global__ void __launch_bounds__(Plan<N>::TPT, Plan<N>::MINB_SYNTH) mask_istft_
                 for (int i = 0; i < G::KEEP; ++i) acc[s][i] = cur[i + G::ADV];
 #pragma unroll
                 for (int i = 0; i < KI; ++i) { ga[i] = ga_n[i]; gb[i] = gb_n[i]; }
-                __syncthreads();
+                __syncthreads();                    // Y (read by the last pass) is rewritten by the next source's pack
             }
         }
         base += G::ADV;

@@ -249,8 +249,8 @@ def test_streaming_and_generic_paths_agree(T, ops):
             assert R.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6, f"path {path}"
 
 
-@pytest.mark.parametrize("N,H", [(256, 64), (256, 128), (1024, 256), (1024, 512), (2048, 512), (2048, 1024),
-                                 (4096, 512), (4096, 1024), (4096, 2048)])
+@pytest.mark.parametrize("N,H", [(256, 32), (256, 64), (256, 128), (1024, 128), (1024, 256), (1024, 512),
+                                 (2048, 256), (2048, 512), (2048, 1024), (4096, 512), (4096, 1024), (4096, 2048)])
 def test_team_kernels_all_sizes(T, ops, N, H):
     """every (N, hop) the shared-memory team kernels cover: all three ops against the oracle, ragged length,
     several chunks per row (long rows), S = 1..4, and the per-frame fallback as a second opinion."""
@@ -275,6 +275,15 @@ def test_team_kernels_all_sizes(T, ops, N, H):
             assert R.rel_l2(ops.mask_istft(xd, md, N, H).cpu().numpy(), y) < 2e-6
         finally:
             _native.set_path(0)
+    # both evaluations of the fused to_log / to_exp gains (polynomial when the warp's magnitudes are small, libm otherwise)
+    x = speechish(rng, 2, 6 * N + 3)
+    for scale in (1.0, 40.0):
+        xs = (x * np.float32(scale)).astype(np.float32)
+        assert R.rel_l2(ops.stft_log(dev(T, xs), N, H).cpu().numpy(), R.to_log_signal(R.stft_feature_np(xs, N, H))) < REL_L2
+    for scale in (0.05, 2.0):
+        feat = (rng.normal(size=(2, 9, N)) * scale).astype(np.float32)
+        ref = R.istft_feature_np(R.to_exp_signal(feat.astype(np.float64)), H, np.float64)
+        assert R.rel_l2(ops.istft(dev(T, feat), H, exp=True).cpu().numpy(), ref) < REL_L2
 
 
 # --------------------------------------------------------------------------
