@@ -6,7 +6,8 @@ import torch
 from gan_sass_tf_b200.app import ops
 from gan_sass_tf_b200 import _native
 
-N, H, B, n = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 else (512, 128, 256, 48000)
+N, H, B, n = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 and sys.argv[1].isdigit() else (512, 128, 256, 48000)
+_native.set_path(int(os.environ.get("GSS_PATH", "0")))      # 1: no register-exchange kernels, 2: per-frame fallback only
 T, _ = _native.frame_count(n, N, H)
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
