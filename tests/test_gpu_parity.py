@@ -459,3 +459,28 @@ def test_spectral_pipeline_pcm16(T, ops):
         assert g.dtype == np.int16 and g.shape == ref_pcm.shape
         assert np.max(np.abs(g.astype(np.int32) - ref_pcm.astype(np.int32))) <= 1, f"batch {k}"
     assert pipe.h2d_bytes == B * n * 2 and pipe.d2h_bytes == B * S * pipe.L * 2
+
+
+def test_cuda_graph_capture_and_replay(T, ops):
+    """the device entry points only enqueue on the caller's stream (no allocation, no sync after the first call),
+    so a step can be captured once into a CUDA graph and replayed on new data in the same buffers."""
+    N, H, n, B, S = 512, 128, 9000, 4, 3
+    rng = np.random.default_rng(31)
+    Tn, _ = R.frame_count(n, N, H)
+    x = T.zeros(B, n, device="cuda")
+    m = T.zeros(B, S, Tn, N // 2, device="cuda")
+    out = T.empty(B * S, (Tn - 1) * H, device="cuda")
+    ops.stft_log(x, N, H); ops.mask_istft(x, m, N, H, out=out)          # first call: per-device table fill
+    T.cuda.synchronize()
+    g = T.cuda.CUDAGraph()
+    with T.cuda.graph(g):
+        feat = ops.stft_log(x, N, H)
+        ops.mask_istft(x, m, N, H, out=out)
+    for seed in (1, 2):
+        xs = speechish(np.random.default_rng(seed), B, n)
+        ms = rng.random((B, S, Tn, N // 2)).astype(np.float32)
+        x.copy_(dev(T, xs)); m.copy_(dev(T, ms))
+        g.replay()
+        T.cuda.synchronize()
+        assert R.rel_l2(feat.cpu().numpy(), R.to_log_signal(R.stft_feature_np(xs, N, H))) < REL_L2
+        assert R.rel_l2(out.cpu().numpy(), R.mask_istft_np(xs, ms, N, H).reshape(B * S, -1)) < REL_L2
