@@ -48,11 +48,11 @@ int sm_count() {
     return sms[dev];
 }
 
-// kernel families: 0 = automatic (N = 512: register-exchange streaming kernels of gss_stream.cuh; other sizes:
+// kernel families: 0 = automatic (N = 256, 512: register-exchange streaming kernels of gss_stream.cuh; other sizes:
 // the shared-memory-FFT streaming kernels of gss_team.cuh; whatever those do not cover: gss_generic.cuh),
 // 1 = never the N = 512 register kernels, 2 = gss_generic.cuh only (cross-check paths for the tests)
 std::atomic<int> g_force_generic{0};
-bool fast_n(int N) { return N == 512 && !g_force_generic.load(std::memory_order_relaxed); }   // register-streaming kernels
+bool fast_n(int N) { return (N == 512 || N == 256) && !g_force_generic.load(std::memory_order_relaxed); }   // register-streaming kernels
 // hop in slots for the team kernels (slot = N/R0 samples: 32, 64, 64, 128, 256), 0 when (N, H) is not covered
 int team_hs(int N, int H) {
     if (g_force_generic.load(std::memory_order_relaxed) >= 2) return 0;
@@ -100,10 +100,10 @@ gss::ChunkPlan plan_chunks(int64_t rows, int npairs, int halo, int64_t slots) {
 }
 
 template <typename K>
-int64_t team_slots(K kernel, int warps, size_t smem) {
+int64_t team_slots(K kernel, int warps, int teams, size_t smem) {
     int nb = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, warps * 32, smem) != cudaSuccess || nb < 1) nb = 1;
-    return (int64_t)sm_count() * nb * warps;
+    return (int64_t)sm_count() * nb * teams;
 }
 
 constexpr int WARPS = 4;
@@ -123,7 +123,8 @@ int ensure_tables(cudaStream_t st) {
     if (ready[dev].load(std::memory_order_acquire)) return GSS_OK;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    gss::tables_kernel<512><<<1, 32, 0, st>>>();
+    gss::tables_kernel<512><<<1, gss::Geo<512>::TPF, 0, st>>>();
+    gss::tables_kernel<256><<<1, gss::Geo<256>::TPF, 0, st>>>();
     CK(cudaGetLastError());
     if (cap != cudaStreamCaptureStatusNone) return GSS_OK;
     CK(cudaStreamSynchronize(st));
@@ -233,13 +234,14 @@ int team_synth(gss::team::SynthArgs a, cudaStream_t st) {
 template <int N, int HS, bool LOG, typename TIn, int WARPS = 4>
 int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
     auto k = gss::stft_kernel<N, HS, LOG, TIn, WARPS>;
-    const size_t smem = team_smem<N>(WARPS);
+    constexpr int TEAMS = WARPS * 32 / gss::Geo<N>::TPF;       // transforms in flight per CTA
+    const size_t smem = team_smem<N>(TEAMS);
     if (int rc = prep(k, smem)) return rc;
     if (int rc = ensure_tables(st)) return rc;
-    gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, team_slots(k, WARPS, smem));
+    gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, team_slots(k, WARPS, TEAMS, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.B * a.nchunk;
-    k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
+    k<<<(unsigned)((items + TEAMS - 1) / TEAMS), WARPS * 32, smem, st>>>(a);
     return after_launch("stft_kernel");
 }
 #ifdef GSS_TUNE
@@ -290,7 +292,7 @@ int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int 
     }
     const bool lg = flags & GSS_FLAG_LOG;
 #define GSS_CASE(NN, HH) if (N == NN && hs == HH) return lg ? launch_stft<NN, HH, true, TIn>(a, st) : launch_stft<NN, HH, false, TIn>(a, st);
-    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
+    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4) GSS_CASE(256, 1) GSS_CASE(256, 2) GSS_CASE(256, 4)
 #undef GSS_CASE
     return fail(GSS_EUNSUPPORTED, "stft: no kernel for N=%d H=%d", N, H);
 }
@@ -299,13 +301,14 @@ int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int 
 template <int N, int HS, bool EXP>
 int launch_istft(gss::IstftArgs a, cudaStream_t st) {
     auto k = gss::istft_kernel<N, HS, EXP, WARPS>;
-    const size_t smem = team_smem<N>(WARPS);
+    constexpr int TEAMS = WARPS * 32 / gss::Geo<N>::TPF;
+    const size_t smem = team_smem<N>(TEAMS);
     if (int rc = prep(k, smem)) return rc;
     if (int rc = ensure_tables(st)) return rc;
-    gss::ChunkPlan pl = plan_chunks(a.rows, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, smem));
+    gss::ChunkPlan pl = plan_chunks(a.rows, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, TEAMS, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.rows * a.nchunk;
-    k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
+    k<<<(unsigned)((items + TEAMS - 1) / TEAMS), WARPS * 32, smem, st>>>(a);
     return after_launch("istft_kernel");
 }
 
@@ -313,7 +316,8 @@ int launch_istft(gss::IstftArgs a, cudaStream_t st) {
 template <int N, int HS, int ST, int WARPS = 4>
 int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
     auto k = gss::mask_istft_kernel<N, HS, ST, WARPS>;
-    size_t smem = gss::SynthSmem<N, ST>::bytes(WARPS);
+    constexpr int TEAMS = WARPS * 32 / gss::Geo<N>::TPF;
+    size_t smem = gss::SynthSmem<N, ST>::bytes(TEAMS);
 #ifdef GSS_TUNE
     smem += (size_t)tune("GSS_EXTRA_SMEM", 0);      // occupancy limiter for single-warp-per-SMSP experiments
 #endif
@@ -325,10 +329,10 @@ int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
     if (!tbuf) cudaMalloc(&tbuf, sizeof(long long) * 8 * 65536);
     a.timing = tbuf;
 #endif
-    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, smem));
+    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, TEAMS, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.B * a.ngroups * a.nchunk;
-    k<<<(unsigned)((items + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(a);
+    k<<<(unsigned)((items + TEAMS - 1) / TEAMS), WARPS * 32, smem, st>>>(a);
 #ifdef GSS_TIMING
     {
         static int calls = 0;
@@ -383,11 +387,13 @@ int synth_variant() {       // 0 = one warp per pair (gss_stream.cuh), 1 = role-
 
 template <int N, int HS>
 int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
-    if (synth_variant() == 1) {
-        if (a.S % 3 == 0) return launch_synth_split<N, HS, 3>(a, st);
-        if (a.S % 2 == 0) return launch_synth_split<N, HS, 2>(a, st);
-        if (a.S == 1) return launch_synth_split<N, HS, 1>(a, st);
-        return launch_synth_split<N, HS, 3>(a, st);
+    if constexpr (N == 512) {
+        if (synth_variant() == 1) {
+            if (a.S % 3 == 0) return launch_synth_split<N, HS, 3>(a, st);
+            if (a.S % 2 == 0) return launch_synth_split<N, HS, 2>(a, st);
+            if (a.S == 1) return launch_synth_split<N, HS, 1>(a, st);
+            return launch_synth_split<N, HS, 3>(a, st);
+        }
     }
     // sources carried per pass: 3 when S is a multiple of 3, else 2 (S even) or 1
     if (a.S % 3 == 0) return launch_synth<N, HS, 3>(a, st);
@@ -515,7 +521,7 @@ int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H, int 
     }
     const bool ex = flags & GSS_FLAG_EXP;
 #define GSS_CASE(NN, HH) if (N == NN && hs == HH) return ex ? launch_istft<NN, HH, true>(a, st) : launch_istft<NN, HH, false>(a, st);
-    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
+    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4) GSS_CASE(256, 1) GSS_CASE(256, 2) GSS_CASE(256, 4)
 #undef GSS_CASE
     return fail(GSS_EUNSUPPORTED, "istft: no kernel for N=%d H=%d", N, H);
 }
@@ -552,7 +558,7 @@ int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64
         return launch_ola_generic<true>(g, st);
     }
 #define GSS_CASE(NN, HH) if (N == NN && hs == HH) return synth_by_s<NN, HH>(a, st);
-    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4)
+    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4) GSS_CASE(256, 1) GSS_CASE(256, 2) GSS_CASE(256, 4)
 #undef GSS_CASE
     return fail(GSS_EUNSUPPORTED, "mask_istft: no kernel for N=%d H=%d", N, H);
 }

@@ -3,8 +3,9 @@
 // Geometry (modelled one-to-one, including the shared-memory layouts and their bank-conflict
 // counts, in tools/fft_model.py and checked on the host by tests/test_fft_model.py):
 //
-//   N = 64*M complex points, M in {4, 8, 16};  a "team" of TPF = N/16 threads owns
-//   one transform, 16 complex points per thread, three passes radix 8 / M / 8.
+//   N = 64*M complex points, M in {4, 8} (N = 256, 512; 16 is modelled only);  a "team" of TPF = N/16
+//   threads (half a warp / one warp) owns one transform, 16 complex points per thread, three passes
+//   radix 8 / M / 8.
 //   L = N/8.  All arithmetic is packed FP32x2 (FADD2/FMUL2/FFMA2): a v2 holds the
 //   same quantity for the two butterflies a thread owns in a pass.
 //
@@ -121,7 +122,8 @@ struct Geo {
     static constexpr int E0_F4 = 8 * P0;      // float4-equivalents (both planes)
     static constexpr int E1_PLANE = 8 * P1;   // floats per plane
     static constexpr int TEAM_FLOATS = E0_F4 * 4 + 2 * E1_PLANE;
-    static_assert(M == 8, "this round implements N = 512 (M = 8); 256/1024 are wired in fft_model.py only");
+    static_assert(M == 8 || M == 4, "implemented: N = 512 (M = 8, one warp per transform) and N = 256 (M = 4, half a warp); "
+                                    "1024 is wired in fft_model.py only");
 };
 
 // per-thread constants of a team member
@@ -133,6 +135,7 @@ struct TeamCtx {
     float* e1;        // team exchange buffer 1 (re plane, im plane at +E1_PLANE)
     cv2 tw0[8];       // pass-0 twiddles W_N^{(2j+e)*k0}, k0 = 1..7 ([0] unused)
     cv2 tw1[3];       // middle twiddles W_L^{(2q+e)*k1} for k1 = 1, 2, 4, q = j % 4
+    unsigned mask;    // lanes of this team inside its warp (all 32 at N = 512, one half at N = 256)
 };
 
 // the seven twiddles w^1..w^7 from the stored w^1, w^2, w^4 (4 complex products)
@@ -144,7 +147,15 @@ __device__ __forceinline__ void expand_tw(const cv2 (&b)[3], cv2 (&w)[8]) {
     w[7] = cmul<false>(w[3], b[2]);
 }
 
-__device__ __forceinline__ void team_sync() { __syncwarp(); }
+// teams never span warps (TPF <= 32): a team-scoped __syncwarp keeps the two half-warp teams of N = 256 independent
+template <int N>
+__device__ __forceinline__ void team_sync(const TeamCtx<N>& c) { __syncwarp(c.mask); }
+template <int N>
+__device__ __forceinline__ unsigned team_mask() {
+    constexpr int TPF = Geo<N>::TPF;
+    if (TPF >= 32) return 0xffffffffu;
+    return ((1u << TPF) - 1u) << ((threadIdx.x & 31) / TPF * TPF);
+}
 
 template <int N>
 __device__ __forceinline__ void team_init(TeamCtx<N>& c, int j, float* team_smem) {
@@ -154,6 +165,7 @@ __device__ __forceinline__ void team_init(TeamCtx<N>& c, int j, float* team_smem
     c.cB = j ? G::L - j : G::L / 2;
     c.e0 = reinterpret_cast<v2*>(team_smem);
     c.e1 = team_smem + G::E0_F4 * 4;
+    c.mask = team_mask<N>();
     const int q = j & 3;
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
@@ -182,7 +194,11 @@ constexpr int TAB_TW0 = 0;        // [k0-1][re/im] : 14 rows
 constexpr int TAB_TW1 = 14;       // [b][re/im]    : 6 rows
 constexpr int TAB_WIN = 20;       // [n0]          : 8 rows (unscaled periodic Hann at samples 2j+e + L*n0)
 constexpr int TAB_ROWS = 28;
-__device__ v2 g_lane_tab[TAB_ROWS][32];
+__device__ v2 g_lane_tab512[TAB_ROWS][32];
+__device__ v2 g_lane_tab256[TAB_ROWS][16];
+template <int N> __device__ __forceinline__ v2& lane_tab(int row, int j) {
+    if constexpr (N == 512) return g_lane_tab512[row][j]; else return g_lane_tab256[row][j];
+}
 
 template <int N>
 __global__ void tables_kernel() {
@@ -190,14 +206,14 @@ __global__ void tables_kernel() {
     TeamCtx<N> c;
     team_init<N>(c, j, nullptr);
 #pragma unroll
-    for (int k0 = 1; k0 < 8; ++k0) { g_lane_tab[TAB_TW0 + 2 * (k0 - 1)][j] = c.tw0[k0].re; g_lane_tab[TAB_TW0 + 2 * (k0 - 1) + 1][j] = c.tw0[k0].im; }
+    for (int k0 = 1; k0 < 8; ++k0) { lane_tab<N>(TAB_TW0 + 2 * (k0 - 1), j) = c.tw0[k0].re; lane_tab<N>(TAB_TW0 + 2 * (k0 - 1) + 1, j) = c.tw0[k0].im; }
 #pragma unroll
-    for (int b = 0; b < 3; ++b) { g_lane_tab[TAB_TW1 + 2 * b][j] = c.tw1[b].re; g_lane_tab[TAB_TW1 + 2 * b + 1][j] = c.tw1[b].im; }
+    for (int b = 0; b < 3; ++b) { lane_tab<N>(TAB_TW1 + 2 * b, j) = c.tw1[b].re; lane_tab<N>(TAB_TW1 + 2 * b + 1, j) = c.tw1[b].im; }
 #pragma unroll
     for (int n0 = 0; n0 < 8; ++n0) {
         const int i0 = 2 * j + Geo<N>::L * n0;
-        g_lane_tab[TAB_WIN + n0][j] = make_float2(0.5f - 0.5f * cospif(2.0f * (float)i0 / (float)N),
-                                                  0.5f - 0.5f * cospif(2.0f * (float)(i0 + 1) / (float)N));
+        lane_tab<N>(TAB_WIN + n0, j) = make_float2(0.5f - 0.5f * cospif(2.0f * (float)i0 / (float)N),
+                                                   0.5f - 0.5f * cospif(2.0f * (float)(i0 + 1) / (float)N));
     }
 }
 
@@ -209,15 +225,17 @@ __device__ __forceinline__ void team_init_tab(TeamCtx<N>& c, int j, float* team_
     c.cB = j ? G::L - j : G::L / 2;
     c.e0 = reinterpret_cast<v2*>(team_smem);
     c.e1 = team_smem + G::E0_F4 * 4;
+    c.mask = team_mask<N>();
 #pragma unroll
-    for (int k0 = 1; k0 < 8; ++k0) { c.tw0[k0].re = g_lane_tab[TAB_TW0 + 2 * (k0 - 1)][j]; c.tw0[k0].im = g_lane_tab[TAB_TW0 + 2 * (k0 - 1) + 1][j]; }
+    for (int k0 = 1; k0 < 8; ++k0) { c.tw0[k0].re = lane_tab<N>(TAB_TW0 + 2 * (k0 - 1), j); c.tw0[k0].im = lane_tab<N>(TAB_TW0 + 2 * (k0 - 1) + 1, j); }
 #pragma unroll
-    for (int b = 0; b < 3; ++b) { c.tw1[b].re = g_lane_tab[TAB_TW1 + 2 * b][j]; c.tw1[b].im = g_lane_tab[TAB_TW1 + 2 * b + 1][j]; }
+    for (int b = 0; b < 3; ++b) { c.tw1[b].re = lane_tab<N>(TAB_TW1 + 2 * b, j); c.tw1[b].im = lane_tab<N>(TAB_TW1 + 2 * b + 1, j); }
 }
 // analysis / synthesis window (scaled) at this lane's sample positions, from the table
+template <int N>
 __device__ __forceinline__ void window_tab(int j, float scale, v2 (&w)[8]) {
 #pragma unroll
-    for (int n0 = 0; n0 < 8; ++n0) w[n0] = vmul(g_lane_tab[TAB_WIN + n0][j], vset(scale));
+    for (int n0 = 0; n0 < 8; ++n0) w[n0] = vmul(lane_tab<N>(TAB_WIN + n0, j), vset(scale));
 }
 
 // ---------------------------------------------------------------------------
@@ -230,7 +248,7 @@ template <int N>
 __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
     typedef Geo<N> G;
     const int j = c.j;
-    team_sync();   // the previous transform's last read of the exchange buffers
+    team_sync(c);   // the previous transform's last read of the exchange buffers
     dft8<false>(a);
     c.e0[j] = a[0].re; c.e0[G::E0_PLANE + j] = a[0].im;
     {
@@ -240,8 +258,8 @@ __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
             c.e0[k0 * G::P0 + j] = t.re; c.e0[G::E0_PLANE + k0 * G::P0 + j] = t.im;
         }
     }
-    team_sync();
-    {   // middle (M = 8): thread (k0 = j/4, q = j%4), lanes n2 = 2q+e
+    team_sync(c);
+    if constexpr (G::M == 8) {   // middle: thread (k0 = j/4, q = j%4), lanes n2 = 2q+e, one packed DFT-8 over n1
         const int k0 = j >> 2, q = j & 3;
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
@@ -261,8 +279,34 @@ __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
             re0[8 * k1] = t.re.x; re1[8 * k1] = t.re.y;
             re0[8 * k1 + G::E1_PLANE] = t.im.x; re1[8 * k1 + G::E1_PLANE] = t.im.y;
         }
+    } else {                     // M = 4: two packed DFT-4 over n1, for k0 = j/4 and j/4 + 4
+        const int kb = j >> 2, q = j & 3;
+        const cv2 w3 = cmul<false>(c.tw1[0], c.tw1[1]);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int k0 = kb + 4 * g;
+#pragma unroll
+            for (int n1 = 0; n1 < 4; ++n1) {
+                a[4 * g + n1].re = c.e0[k0 * G::P0 + 4 * n1 + q];
+                a[4 * g + n1].im = c.e0[G::E0_PLANE + k0 * G::P0 + 4 * n1 + q];
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int k0 = kb + 4 * g;
+            cv2 b[4] = {a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]};
+            dft4<false>(b);
+            b[1] = cmul<false>(b[1], c.tw1[0]); b[2] = cmul<false>(b[2], c.tw1[1]); b[3] = cmul<false>(b[3], w3);
+            float* re0 = c.e1 + (2 * q) * G::P1 + k0;
+            float* re1 = re0 + G::P1;
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) {
+                re0[8 * k1] = b[k1].re.x; re1[8 * k1] = b[k1].re.y;
+                re0[8 * k1 + G::E1_PLANE] = b[k1].im.x; re1[8 * k1 + G::E1_PLANE] = b[k1].im.y;
+            }
+        }
     }
-    team_sync();
+    team_sync(c);
 #pragma unroll
     for (int n2 = 0; n2 < 8; ++n2) {
         const float* p = c.e1 + n2 * G::P1;
@@ -278,7 +322,7 @@ template <int N>
 __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8]) {
     typedef Geo<N> G;
     const int j = c.j;
-    team_sync();   // the previous transform's last read of the exchange buffers
+    team_sync(c);   // the previous transform's last read of the exchange buffers
     dft8<true>(a);
 #pragma unroll
     for (int n2 = 0; n2 < 8; ++n2) {
@@ -286,8 +330,8 @@ __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8]) {
         p[c.cA] = a[n2].re.x; p[c.cB] = a[n2].re.y;
         p[c.cA + G::E1_PLANE] = a[n2].im.x; p[c.cB + G::E1_PLANE] = a[n2].im.y;
     }
-    team_sync();
-    {
+    team_sync(c);
+    if constexpr (G::M == 8) {
         const int k0 = j >> 2, q = j & 3;
         const float* re0 = c.e1 + (2 * q) * G::P1 + k0;
         const float* re1 = re0 + G::P1;
@@ -306,8 +350,28 @@ __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8]) {
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1)
         { c.e0[k0 * G::P0 + 4 * n1 + q] = a[n1].re; c.e0[G::E0_PLANE + k0 * G::P0 + 4 * n1 + q] = a[n1].im; }
+    } else {                     // M = 4: two packed inverse DFT-4, for k0 = j/4 and j/4 + 4
+        const int kb = j >> 2, q = j & 3;
+        const cv2 w3 = cmul<false>(c.tw1[0], c.tw1[1]);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int k0 = kb + 4 * g;
+            const float* re0 = c.e1 + (2 * q) * G::P1 + k0;
+            const float* re1 = re0 + G::P1;
+            cv2 b[4];
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) {
+                b[k1].re = make_float2(re0[8 * k1], re1[8 * k1]);
+                b[k1].im = make_float2(re0[8 * k1 + G::E1_PLANE], re1[8 * k1 + G::E1_PLANE]);
+            }
+            b[1] = cmul<true>(b[1], c.tw1[0]); b[2] = cmul<true>(b[2], c.tw1[1]); b[3] = cmul<true>(b[3], w3);
+            dft4<true>(b);
+#pragma unroll
+            for (int n1 = 0; n1 < 4; ++n1)
+            { c.e0[k0 * G::P0 + 4 * n1 + q] = b[n1].re; c.e0[G::E0_PLANE + k0 * G::P0 + 4 * n1 + q] = b[n1].im; }
+        }
     }
-    team_sync();
+    team_sync(c);
     {
         a[0].re = c.e0[j]; a[0].im = c.e0[G::E0_PLANE + j];
 #pragma unroll

@@ -70,7 +70,7 @@ __global__ void __maxnreg__(168) mask_istft_split_kernel(const SynthArgs p) {
     TeamCtx<N> ctx;
     team_init_tab<N>(ctx, j, team);
     v2 win[8];
-    window_tab(j, 1.0f / (float)N, win);
+    window_tab<N>(j, 1.0f / (float)N, win);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ analysis role

@@ -376,8 +376,9 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((6
     typedef SGeo<N, HS> SG; typedef Geo<N> G;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
-    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
-    const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
+    constexpr int TEAMS = WARPS * 32 / G::TPF;              // transforms in flight per CTA (two per warp at N = 256)
+    const int warp = threadIdx.x / G::TPF, j = threadIdx.x % G::TPF;
+    const int64_t item = (int64_t)blockIdx.x * TEAMS + warp;
     if (item >= p.B * p.nchunk) return;
     const int64_t b = item / p.nchunk;
     const int c = (int)(item - b * p.nchunk);
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((6
     TeamCtx<N> ctx;
     team_init_tab<N>(ctx, j, smf + warp * G::TEAM_FLOATS);
     v2 win[8];
-    window_tab(j, 1.0f / (float)N, win);           // 1/sum(w) = 2/N, and the 1/2 of the two-for-one split
+    window_tab<N>(j, 1.0f / (float)N, win);        // 1/sum(w) = 2/N, and the 1/2 of the two-for-one split
 
     const TIn* row = p.wave + b * p.ld;
     const bool al = p.al_in != 0;
@@ -431,21 +432,21 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((6
                 a2b[i] = vfma(s.br[i], s.br[i], vmul(s.bi[i], s.bi[i]));
                 mx = fmaxf(fmaxf(mx, fmaxf(a2a[i].x, a2a[i].y)), fmaxf(a2b[i].x, a2b[i].y));
             }
-            if (__all_sync(0xffffffffu, mx <= 0.015625f)) {
+            if (__all_sync(ctx.mask, mx <= 0.015625f)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     v2 ga = log_gain2_micro(a2a[i], p.eps), gb = log_gain2_micro(a2b[i], p.eps);
                     s.ar[i] = vmul(s.ar[i], ga); s.ai[i] = vmul(s.ai[i], ga);
                     s.br[i] = vmul(s.br[i], gb); s.bi[i] = vmul(s.bi[i], gb);
                 }
-            } else if (__all_sync(0xffffffffu, mx <= 0.25f)) {
+            } else if (__all_sync(ctx.mask, mx <= 0.25f)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     v2 ga = log_gain2_tiny(a2a[i], p.eps), gb = log_gain2_tiny(a2b[i], p.eps);
                     s.ar[i] = vmul(s.ar[i], ga); s.ai[i] = vmul(s.ai[i], ga);
                     s.br[i] = vmul(s.br[i], gb); s.bi[i] = vmul(s.bi[i], gb);
                 }
-            } else if (__all_sync(0xffffffffu, mx <= 1.0f)) {
+            } else if (__all_sync(ctx.mask, mx <= 1.0f)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     v2 ga = log_gain2_small(a2a[i], p.eps), gb = log_gain2_small(a2b[i], p.eps);
@@ -505,8 +506,9 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     typedef SGeo<N, HS> SG; typedef Geo<N> G;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
-    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
-    const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
+    constexpr int TEAMS = WARPS * 32 / G::TPF;
+    const int warp = threadIdx.x / G::TPF, j = threadIdx.x % G::TPF;
+    const int64_t item = (int64_t)blockIdx.x * TEAMS + warp;
     if (item >= p.rows * p.nchunk) return;
     const int64_t r = item / p.nchunk;
     const int c = (int)(item - r * p.nchunk);
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     team_init_tab<N>(ctx, j, smf + warp * G::TEAM_FLOATS);
     v2 win[8];
     // frame = sum(w) * irfft = (N/2)(1/N) * raw inverse: the 1/2 and 1/sum(w^2) are applied at the store
-    window_tab(j, 1.0f, win);
+    window_tab<N>(j, 1.0f, win);
     OlaOut<SG> o;
     o.init(p.T, j, p.al_out != 0, 1.0f);
     float* orow = p.out + r * p.ld_out;
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
                 eb[i] = vfma(ybr[i], ybr[i], vfma(ybi[i], ybi[i], vset(p.eps)));
                 mx = fmaxf(fmaxf(mx, fmaxf(ea[i].x, ea[i].y)), fmaxf(eb[i].x, eb[i].y));
             }
-            if (__all_sync(0xffffffffu, mx < 1.0f)) {
+            if (__all_sync(ctx.mask, mx < 1.0f)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const v2 ga = exp_gain2_small(ea[i]), gb = exp_gain2_small(eb[i]);
@@ -663,13 +665,14 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
     constexpr int NH = N / 2;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
-    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
+    constexpr int TEAMS = WARPS * 32 / G::TPF;
+    const int warp = threadIdx.x / G::TPF, j = threadIdx.x % G::TPF;       // team index inside the CTA, lane inside the team
     float* team = smf + warp * SM::TEAM_FLOATS;
     float* stage = team + G::TEAM_FLOATS;                                  // 2 x STAGE_FLOATS, 16-byte aligned
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smf + WARPS * SM::TEAM_FLOATS) + 2 * warp;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smf + TEAMS * SM::TEAM_FLOATS) + 2 * warp;
     if (j == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
-    const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t item = (int64_t)blockIdx.x * TEAMS + warp;
     const int64_t per_b = (int64_t)p.ngroups * p.nchunk;
     if (item >= p.B * per_b) return;
     const int64_t b = item / per_b;
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
     TeamCtx<N> ctx;
     team_init_tab<N>(ctx, j, team);
     v2 win[8];                                     // hann / N: analysis scale; synthesis rescaled at the store
-    window_tab(j, 1.0f / (float)N, win);
+    window_tab<N>(j, 1.0f / (float)N, win);
 
     OlaOut<SG> o;
     o.init(p.T, j, p.al_out != 0, (float)N);
@@ -696,7 +699,8 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
     // 32-bit values so that the elected lane only moves them to uniform registers)
     const uint32_t stage_s = smem_u32(stage), bars_s = smem_u32(bars);
     auto prefetch = [&](int q) {
-        if (elect_one()) {
+        // one lane per team: the hardware-elected one when the team is the whole warp, lane 0 of each half otherwise
+        if (G::TPF >= 32 ? elect_one() : j == 0) {
             const uint32_t st = (uint32_t)(q - qs) & 1u;
             const int64_t ta = 2 * (int64_t)q;
             const uint32_t bytes = (ta + 1 < p.T ? 2 : 1) * NH * (uint32_t)sizeof(float);
