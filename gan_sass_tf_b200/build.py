@@ -2,6 +2,11 @@
 
 ``python -m gan_sass_tf_b200.build`` - in-tree, so the library travels with the
 source tree to the GPU box.  nvcc cross-compiles without a GPU.
+
+``csrc/gss_api.cu`` is compiled five times with ``-DGSS_PART=0..4`` (C ABI + element-wise
+kernels / streaming kernels N = 512 / N = 256 / team kernels N <= 1024 / N >= 2048), in
+parallel, and the objects are linked into one shared library: ~170 kernel instances in
+about two minutes instead of five.
 """
 from __future__ import annotations
 
@@ -9,17 +14,20 @@ import os
 import shutil
 import subprocess
 import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libgss.so")
-SOURCES = ["gss_api.cu"]
+SOURCE = "gss_api.cu"
+PARTS = (0, 1, 2, 3, 4)
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "gss_api.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -34,20 +42,34 @@ def stale() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, f) for f in [SOURCE] + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd, verbose):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    nvcc = _nvcc()
+    src = os.path.join(CSRC, SOURCE)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    obj_dir = tempfile.mkdtemp(prefix="gss_obj_")          # objects stay out of the tree (only the .so travels)
+    try:
+        objs = [os.path.join(obj_dir, f"gss_part{k}.o") for k in PARTS]
+        cmds = [[nvcc] + NVCC_FLAGS + extra + [f"-DGSS_PART={k}", "-c", src, "-o", o] for k, o in zip(PARTS, objs)]
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as ex:
+            list(ex.map(lambda c: _run(c, verbose), cmds))
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs, verbose)
+    finally:
+        shutil.rmtree(obj_dir, ignore_errors=True)
     return OUT
 
 

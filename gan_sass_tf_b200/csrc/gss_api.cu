@@ -11,16 +11,58 @@
 #include <cuda_runtime.h>
 
 #include "../../include/gss_api.h"
-#include "gss_elem.cuh"
-#include "gss_generic.cuh"
 #include "gss_stream.cuh"
 #include "gss_team.cuh"
 #include "gss_split.cuh"
 
-namespace {
+// The library is one source compiled in several parts (GSS_PART = 0..4, see gan_sass_tf_b200/build.py) so that
+// the ~170 kernel instances build in parallel: part 0 = the C ABI, element-wise kernels, copy pipelines and the
+// per-frame fallback; 1 / 2 = register-exchange streaming kernels for N = 512 / 256; 3 / 4 = team kernels for
+// N <= 1024 / >= 2048.  Without GSS_PART everything is one translation unit (tools/regs.sh).  Helpers below are
+// per-part copies (namespace gss_part_<k>); the state they share lives in inline variables.
+#ifndef GSS_PART
+#define GSS_PART 9                 // everything in one translation unit
+#endif
+#define GSS_HAS(p) (GSS_PART == 9 || GSS_PART == (p))
+// nvcc names an anonymous namespace after the source file, so the per-part helper copies need distinct names
+#define GSS_CAT_(a, b) a##b
+#define GSS_CAT(a, b) GSS_CAT_(a, b)
+#define GSS_NS GSS_CAT(gss_part_, GSS_PART)
+#if GSS_HAS(0)
+#include "gss_elem.cuh"          // non-template kernels: defined in part 0 only
+#include "gss_generic.cuh"
+#endif
 
-thread_local std::string g_err;
-std::atomic<int64_t> g_launches{0};
+namespace gss_shared {
+inline thread_local std::string g_err;
+inline std::atomic<int64_t> g_launches{0};
+inline std::atomic<int> g_force_generic{0};
+
+// declared everywhere, each defined in exactly one part
+int stream512_stft_f32(int hs, bool lg, gss::StftArgs<float> a, cudaStream_t st);
+int stream512_stft_i16(int hs, bool lg, gss::StftArgs<int16_t> a, cudaStream_t st);
+int stream512_istft(int hs, bool ex, gss::IstftArgs a, cudaStream_t st);
+int stream512_synth(int hs, gss::SynthArgs a, cudaStream_t st);
+int stream256_stft_f32(int hs, bool lg, gss::StftArgs<float> a, cudaStream_t st);
+int stream256_stft_i16(int hs, bool lg, gss::StftArgs<int16_t> a, cudaStream_t st);
+int stream256_istft(int hs, bool ex, gss::IstftArgs a, cudaStream_t st);
+int stream256_synth(int hs, gss::SynthArgs a, cudaStream_t st);
+int team_lo_stft_f32(int N, int ths, gss::team::StftArgs<float> t, cudaStream_t st);     // N <= 1024
+int team_lo_stft_i16(int N, int ths, gss::team::StftArgs<int16_t> t, cudaStream_t st);
+int team_lo_istft(int N, int ths, gss::team::IstftArgs t, cudaStream_t st);
+int team_lo_synth(int N, int ths, gss::team::SynthArgs t, cudaStream_t st);
+int team_hi_stft_f32(int N, int ths, gss::team::StftArgs<float> t, cudaStream_t st);     // N >= 2048
+int team_hi_stft_i16(int N, int ths, gss::team::StftArgs<int16_t> t, cudaStream_t st);
+int team_hi_istft(int N, int ths, gss::team::IstftArgs t, cudaStream_t st);
+int team_hi_synth(int N, int ths, gss::team::SynthArgs t, cudaStream_t st);
+
+}  // namespace gss_shared
+
+namespace GSS_NS {
+using namespace gss_shared;
+using gss_shared::g_err;
+using gss_shared::g_launches;
+using gss_shared::g_force_generic;
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -51,7 +93,6 @@ int sm_count() {
 // kernel families: 0 = automatic (N = 256, 512: register-exchange streaming kernels of gss_stream.cuh; other sizes:
 // the shared-memory-FFT streaming kernels of gss_team.cuh; whatever those do not cover: gss_generic.cuh),
 // 1 = never the N = 512 register kernels, 2 = gss_generic.cuh only (cross-check paths for the tests)
-std::atomic<int> g_force_generic{0};
 bool fast_n(int N) { return (N == 512 || N == 256) && !g_force_generic.load(std::memory_order_relaxed); }   // register-streaming kernels
 // hop in slots for the team kernels (slot = N/R0 samples: 32, 64, 64, 128, 256), 0 when (N, H) is not covered
 int team_hs(int N, int H) {
@@ -115,6 +156,7 @@ size_t team_smem(int warps) { return sizeof(float) * ((size_t)warps * gss::Geo<N
 // runs on the stream of the first call, followed by one stream synchronisation, so the table is visible
 // to every later launch on any stream; inside a stream capture it is simply recorded into the graph.
 // Not counted by gss_launch_count() (set-up, not one of the path's kernels).
+template <int N>
 int ensure_tables(cudaStream_t st) {
     static std::atomic<int> ready[64];
     int dev = 0;
@@ -123,8 +165,7 @@ int ensure_tables(cudaStream_t st) {
     if (ready[dev].load(std::memory_order_acquire)) return GSS_OK;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    gss::tables_kernel<512><<<1, gss::Geo<512>::TPF, 0, st>>>();
-    gss::tables_kernel<256><<<1, gss::Geo<256>::TPF, 0, st>>>();
+    gss::tables_kernel<N><<<1, gss::Geo<N>::TPF, 0, st>>>();
     CK(cudaGetLastError());
     if (cap != cudaStreamCaptureStatusNone) return GSS_OK;
     CK(cudaStreamSynchronize(st));
@@ -138,6 +179,7 @@ int prep(K kernel, size_t smem) {
     return GSS_OK;
 }
 
+#if GSS_HAS(0)
 // ---- any-size path (gss_generic.cuh) -------------------------------------------
 template <typename TIn>
 int launch_stft_generic(const TIn* wave, int64_t B, int64_t n, int64_t ld, int64_t T, int N, int H, int flags, float eps,
@@ -171,6 +213,8 @@ int launch_ola_generic(gss::gen::OlaArgs a, cudaStream_t st) {
     k<<<grid, gss::gen::THREADS, smem, st>>>(a);
     return after_launch("gen::ola_kernel");
 }
+
+#endif  // GSS_HAS(0)
 
 // ---- team path (gss_team.cuh) -------------------------------------------------------
 template <typename K>
@@ -221,11 +265,14 @@ int team_synth(gss::team::SynthArgs a, cudaStream_t st) {
     return team_synth_st<N, HS, 3>(a, st);
 }
 // F<N, HS>::run(args...) for the (N, hs) pairs the team kernels cover
-#define GSS_TEAM_DISPATCH(N, hs, CALL)                                                                              \
+#define GSS_TEAM_DISPATCH_LO(N, hs, CALL)                                                                           \
     do {                                                                                                            \
         if (N == 256 && hs == 1) { CALL(256, 1) } if (N == 256 && hs == 2) { CALL(256, 2) } if (N == 256 && hs == 4) { CALL(256, 4) }       \
         if (N == 512 && hs == 1) { CALL(512, 1) } if (N == 512 && hs == 2) { CALL(512, 2) } if (N == 512 && hs == 4) { CALL(512, 4) }       \
         if (N == 1024 && hs == 2) { CALL(1024, 2) } if (N == 1024 && hs == 4) { CALL(1024, 4) } if (N == 1024 && hs == 8) { CALL(1024, 8) } \
+    } while (0)
+#define GSS_TEAM_DISPATCH_HI(N, hs, CALL)                                                                           \
+    do {                                                                                                            \
         if (N == 2048 && hs == 2) { CALL(2048, 2) } if (N == 2048 && hs == 4) { CALL(2048, 4) } if (N == 2048 && hs == 8) { CALL(2048, 8) } \
         if (N == 4096 && hs == 2) { CALL(4096, 2) } if (N == 4096 && hs == 4) { CALL(4096, 4) } if (N == 4096 && hs == 8) { CALL(4096, 8) } \
     } while (0)
@@ -237,7 +284,7 @@ int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
     constexpr int TEAMS = WARPS * 32 / gss::Geo<N>::TPF;       // transforms in flight per CTA
     const size_t smem = team_smem<N>(TEAMS);
     if (int rc = prep(k, smem)) return rc;
-    if (int rc = ensure_tables(st)) return rc;
+    if (int rc = ensure_tables<N>(st)) return rc;
     gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, team_slots(k, WARPS, TEAMS, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.B * a.nchunk;
@@ -264,6 +311,7 @@ int launch_stft(gss::StftArgs<TIn> a, cudaStream_t st) {
 #endif
     return launch_stft_w<N, HS, LOG, TIn, 4>(a, st);
 }
+#if GSS_HAS(0)
 template <typename TIn>
 int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int H, int flags, float eps, float* feat, void* stream) {
     int hs = 0;
@@ -284,18 +332,16 @@ int stft_dispatch(const TIn* wave, int64_t B, int64_t n, int64_t ld, int N, int 
             gss::team::StftArgs<TIn> t{};
             t.wave = wave; t.feat = feat; t.B = B; t.n = n; t.ld = ld; t.T = a.T; t.npairs = a.npairs;
             t.log = (flags & GSS_FLAG_LOG) ? 1 : 0; t.eps = eps;
-#define GSS_CALL(NN, HH) return team_stft<NN, HH, TIn>(t, st);
-            GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
-#undef GSS_CALL
+            if constexpr (sizeof(TIn) == 4) return N <= 1024 ? team_lo_stft_f32(N, ths, t, st) : team_hi_stft_f32(N, ths, t, st);
+            else return N <= 1024 ? team_lo_stft_i16(N, ths, t, st) : team_hi_stft_i16(N, ths, t, st);
         }
         return launch_stft_generic<TIn>(wave, B, n, ld, a.T, N, H, flags, eps, feat, st);
     }
     const bool lg = flags & GSS_FLAG_LOG;
-#define GSS_CASE(NN, HH) if (N == NN && hs == HH) return lg ? launch_stft<NN, HH, true, TIn>(a, st) : launch_stft<NN, HH, false, TIn>(a, st);
-    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4) GSS_CASE(256, 1) GSS_CASE(256, 2) GSS_CASE(256, 4)
-#undef GSS_CASE
-    return fail(GSS_EUNSUPPORTED, "stft: no kernel for N=%d H=%d", N, H);
+    if constexpr (sizeof(TIn) == 4) return N == 512 ? stream512_stft_f32(hs, lg, a, st) : stream256_stft_f32(hs, lg, a, st);
+    else return N == 512 ? stream512_stft_i16(hs, lg, a, st) : stream256_stft_i16(hs, lg, a, st);
 }
+#endif  // GSS_HAS(0)
 
 // ---- iSTFT --------------------------------------------------------------
 template <int N, int HS, bool EXP>
@@ -304,7 +350,7 @@ int launch_istft(gss::IstftArgs a, cudaStream_t st) {
     constexpr int TEAMS = WARPS * 32 / gss::Geo<N>::TPF;
     const size_t smem = team_smem<N>(TEAMS);
     if (int rc = prep(k, smem)) return rc;
-    if (int rc = ensure_tables(st)) return rc;
+    if (int rc = ensure_tables<N>(st)) return rc;
     gss::ChunkPlan pl = plan_chunks(a.rows, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, TEAMS, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.rows * a.nchunk;
@@ -322,7 +368,7 @@ int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
     smem += (size_t)tune("GSS_EXTRA_SMEM", 0);      // occupancy limiter for single-warp-per-SMSP experiments
 #endif
     if (int rc = prep(k, smem)) return rc;
-    if (int rc = ensure_tables(st)) return rc;
+    if (int rc = ensure_tables<N>(st)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
 #ifdef GSS_TIMING
     static long long* tbuf = nullptr;
@@ -372,7 +418,7 @@ int launch_synth_split(gss::SynthArgs a, cudaStream_t st) {
     auto k = gss::mask_istft_split_kernel<N, HS, ST>;
     const size_t smem = gss::SplitSmem<N, ST>::bytes();
     if (int rc = prep(k, smem)) return rc;
-    if (int rc = ensure_tables(st)) return rc;
+    if (int rc = ensure_tables<N>(st)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
     gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, cta_slots(k, (1 + ST) * 32, smem));
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
@@ -402,6 +448,62 @@ int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
     if (a.S == 1) return launch_synth<N, HS, 1>(a, st);
     return launch_synth<N, HS, 3>(a, st);
 }
+
+// ---- bridges between the parts (declared in gss_shared at the top of the file) ----------------------
+}  // namespace GSS_NS
+namespace gss_shared {
+using namespace GSS_NS;
+#define GSS_STREAM_PART(NN)                                                                                          \
+    int stream##NN##_stft_f32(int hs, bool lg, gss::StftArgs<float> a, cudaStream_t st) {                            \
+        if (hs == 1) return lg ? launch_stft<NN, 1, true, float>(a, st) : launch_stft<NN, 1, false, float>(a, st);   \
+        if (hs == 2) return lg ? launch_stft<NN, 2, true, float>(a, st) : launch_stft<NN, 2, false, float>(a, st);   \
+        return lg ? launch_stft<NN, 4, true, float>(a, st) : launch_stft<NN, 4, false, float>(a, st);                \
+    }                                                                                                                \
+    int stream##NN##_stft_i16(int hs, bool lg, gss::StftArgs<int16_t> a, cudaStream_t st) {                          \
+        if (hs == 1) return lg ? launch_stft<NN, 1, true, int16_t>(a, st) : launch_stft<NN, 1, false, int16_t>(a, st); \
+        if (hs == 2) return lg ? launch_stft<NN, 2, true, int16_t>(a, st) : launch_stft<NN, 2, false, int16_t>(a, st); \
+        return lg ? launch_stft<NN, 4, true, int16_t>(a, st) : launch_stft<NN, 4, false, int16_t>(a, st);            \
+    }                                                                                                                \
+    int stream##NN##_istft(int hs, bool ex, gss::IstftArgs a, cudaStream_t st) {                                     \
+        if (hs == 1) return ex ? launch_istft<NN, 1, true>(a, st) : launch_istft<NN, 1, false>(a, st);               \
+        if (hs == 2) return ex ? launch_istft<NN, 2, true>(a, st) : launch_istft<NN, 2, false>(a, st);               \
+        return ex ? launch_istft<NN, 4, true>(a, st) : launch_istft<NN, 4, false>(a, st);                            \
+    }                                                                                                                \
+    int stream##NN##_synth(int hs, gss::SynthArgs a, cudaStream_t st) {                                              \
+        if (hs == 1) return synth_by_s<NN, 1>(a, st);                                                                \
+        if (hs == 2) return synth_by_s<NN, 2>(a, st);                                                                \
+        return synth_by_s<NN, 4>(a, st);                                                                             \
+    }
+#if GSS_HAS(1)
+GSS_STREAM_PART(512)
+#endif
+#if GSS_HAS(2)
+GSS_STREAM_PART(256)
+#endif
+#undef GSS_STREAM_PART
+
+#define GSS_TEAM_PART(NAME, DISPATCH)                                                                                \
+    int NAME##_stft_f32(int N, int ths, gss::team::StftArgs<float> t, cudaStream_t st) {                             \
+        DISPATCH(N, ths, GSS_CALL_STFT_F32); return fail(GSS_EUNSUPPORTED, "team stft: no kernel for N=%d", N); }    \
+    int NAME##_stft_i16(int N, int ths, gss::team::StftArgs<int16_t> t, cudaStream_t st) {                           \
+        DISPATCH(N, ths, GSS_CALL_STFT_I16); return fail(GSS_EUNSUPPORTED, "team stft: no kernel for N=%d", N); }    \
+    int NAME##_istft(int N, int ths, gss::team::IstftArgs t, cudaStream_t st) {                                      \
+        DISPATCH(N, ths, GSS_CALL_ISTFT); return fail(GSS_EUNSUPPORTED, "team istft: no kernel for N=%d", N); }      \
+    int NAME##_synth(int N, int ths, gss::team::SynthArgs t, cudaStream_t st) {                                      \
+        DISPATCH(N, ths, GSS_CALL_SYNTH); return fail(GSS_EUNSUPPORTED, "team mask_istft: no kernel for N=%d", N); }
+#define GSS_CALL_STFT_F32(NN, HH) return team_stft<NN, HH, float>(t, st);
+#define GSS_CALL_STFT_I16(NN, HH) return team_stft<NN, HH, int16_t>(t, st);
+#define GSS_CALL_ISTFT(NN, HH) return team_istft<NN, HH>(t, st);
+#define GSS_CALL_SYNTH(NN, HH) return team_synth<NN, HH>(t, st);
+#if GSS_HAS(3)
+GSS_TEAM_PART(team_lo, GSS_TEAM_DISPATCH_LO)
+#endif
+#if GSS_HAS(4)
+GSS_TEAM_PART(team_hi, GSS_TEAM_DISPATCH_HI)
+#endif
+#undef GSS_TEAM_PART
+}  // namespace gss_shared
+namespace GSS_NS {
 
 int grid_for(int64_t work_items, int block) {
     int64_t want = (work_items + block - 1) / block;
@@ -465,8 +567,10 @@ struct CopyStreams {
 };
 thread_local CopyStreams g_cs;
 
-}  // namespace
+}  // namespace GSS_NS
 
+#if GSS_HAS(0)
+using namespace GSS_NS;
 extern "C" {
 
 int gss_version(void) { return 100; }
@@ -510,9 +614,7 @@ int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H, int 
             gss::team::IstftArgs t{};
             t.feat = feat; t.out = wave_out; t.rows = R; t.T = T; t.ld_out = ld_out; t.npairs = a.npairs;
             t.exp = (flags & GSS_FLAG_EXP) ? 1 : 0; t.eps = eps;
-#define GSS_CALL(NN, HH) return team_istft<NN, HH>(t, st);
-            GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
-#undef GSS_CALL
+            return N <= 1024 ? team_lo_istft(N, ths, t, st) : team_hi_istft(N, ths, t, st);
         }
         gss::gen::OlaArgs g{};
         g.feat = feat; g.out = wave_out; g.rows = R; g.T = T; g.ld_out = ld_out; g.N = N; g.H = H; g.S = 1;
@@ -520,10 +622,7 @@ int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H, int 
         return launch_ola_generic<false>(g, st);
     }
     const bool ex = flags & GSS_FLAG_EXP;
-#define GSS_CASE(NN, HH) if (N == NN && hs == HH) return ex ? launch_istft<NN, HH, true>(a, st) : launch_istft<NN, HH, false>(a, st);
-    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4) GSS_CASE(256, 1) GSS_CASE(256, 2) GSS_CASE(256, 4)
-#undef GSS_CASE
-    return fail(GSS_EUNSUPPORTED, "istft: no kernel for N=%d H=%d", N, H);
+    return N == 512 ? stream512_istft(hs, ex, a, st) : stream256_istft(hs, ex, a, st);
 }
 
 int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64_t n, int64_t ld, int N, int H,
@@ -548,19 +647,14 @@ int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64
             gss::team::SynthArgs t{};
             t.wave = wave; t.mask = mask; t.out = out; t.B = B; t.n = n; t.ld = ld; t.T = a.T; t.ld_out = ld_out; t.S = S;
             t.npairs = a.npairs;
-#define GSS_CALL(NN, HH) return team_synth<NN, HH>(t, st);
-            GSS_TEAM_DISPATCH(N, ths, GSS_CALL);
-#undef GSS_CALL
+            return N <= 1024 ? team_lo_synth(N, ths, t, st) : team_hi_synth(N, ths, t, st);
         }
         gss::gen::OlaArgs g{};
         g.wave = wave; g.mask = mask; g.out = out; g.rows = B * S; g.n = n; g.ld = ld; g.T = a.T; g.ld_out = ld_out;
         g.N = N; g.H = H; g.S = S;
         return launch_ola_generic<true>(g, st);
     }
-#define GSS_CASE(NN, HH) if (N == NN && hs == HH) return synth_by_s<NN, HH>(a, st);
-    GSS_CASE(512, 1) GSS_CASE(512, 2) GSS_CASE(512, 4) GSS_CASE(256, 1) GSS_CASE(256, 2) GSS_CASE(256, 4)
-#undef GSS_CASE
-    return fail(GSS_EUNSUPPORTED, "mask_istft: no kernel for N=%d H=%d", N, H);
+    return N == 512 ? stream512_synth(hs, a, st) : stream256_synth(hs, a, st);
 }
 
 int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_t T, int N, float* out, void* stream) {
@@ -832,3 +926,4 @@ int gss_mask_istft_d2h(const float* wave_d, const float* mask_d, int64_t B, int 
 }
 
 }  // extern "C"
+#endif  // GSS_HAS(0)

@@ -194,8 +194,9 @@ constexpr int TAB_TW0 = 0;        // [k0-1][re/im] : 14 rows
 constexpr int TAB_TW1 = 14;       // [b][re/im]    : 6 rows
 constexpr int TAB_WIN = 20;       // [n0]          : 8 rows (unscaled periodic Hann at samples 2j+e + L*n0)
 constexpr int TAB_ROWS = 28;
-__device__ v2 g_lane_tab512[TAB_ROWS][32];
-__device__ v2 g_lane_tab256[TAB_ROWS][16];
+// one copy per translation unit (the library is built in parts): each part fills and reads its own
+static __device__ v2 g_lane_tab512[TAB_ROWS][32];
+static __device__ v2 g_lane_tab256[TAB_ROWS][16];
 template <int N> __device__ __forceinline__ v2& lane_tab(int row, int j) {
     if constexpr (N == 512) return g_lane_tab512[row][j]; else return g_lane_tab256[row][j];
 }
