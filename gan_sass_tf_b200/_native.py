@@ -24,6 +24,7 @@ SIGNATURES = {
     "gss_last_error": (c_char_p, []),
     "gss_launch_count": (c_int64, []),
     "gss_set_path": (c_int, [c_int]),
+    "gss_set_synth_variant": (c_int, [c_int]),
     "gss_supported_fft_sizes": (c_int, [POINTER(c_int), c_int]),
     "gss_frame_count": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "gss_stft_packed": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P]),
@@ -102,6 +103,11 @@ def supported_fft_sizes():
 def set_path(path: int):
     """0 = automatic kernel selection, 1 = any-size shared-memory kernels only."""
     check(lib().gss_set_path(path))
+
+
+def set_synth_variant(variant: int):
+    """N = 512 fused synthesis: 0 = register-resident kernel, 1 = role-split CTAs, 2 = tensor-memory state."""
+    check(lib().gss_set_synth_variant(variant))
 
 
 def launch_count() -> int:

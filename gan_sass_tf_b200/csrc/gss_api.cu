@@ -14,6 +14,7 @@
 #include "gss_stream.cuh"
 #include "gss_team.cuh"
 #include "gss_split.cuh"
+#include "gss_tmem.cuh"
 
 // The library is one source compiled in several parts (GSS_PART = 0..4, see gan_sass_tf_b200/build.py) so that
 // the ~170 kernel instances build in parallel: part 0 = the C ABI, element-wise kernels, copy pipelines and the
@@ -37,6 +38,7 @@ namespace gss_shared {
 inline thread_local std::string g_err;
 inline std::atomic<int64_t> g_launches{0};
 inline std::atomic<int> g_force_generic{0};
+inline std::atomic<int> g_synth_variant{-1};        // -1: not chosen yet (GSS_SYNTH_SPLIT decides on first use)
 
 // declared everywhere, each defined in exactly one part
 int stream512_stft_f32(int hs, bool lg, gss::StftArgs<float> a, cudaStream_t st);
@@ -63,6 +65,7 @@ using namespace gss_shared;
 using gss_shared::g_err;
 using gss_shared::g_launches;
 using gss_shared::g_force_generic;
+using gss_shared::g_synth_variant;
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -425,9 +428,24 @@ int launch_synth_split(gss::SynthArgs a, cudaStream_t st) {
     k<<<(unsigned)(a.B * a.ngroups * a.nchunk), (1 + ST) * 32, smem, st>>>(a);
     return after_launch("mask_istft_split_kernel");
 }
-int synth_variant() {       // 0 = one warp per pair (gss_stream.cuh), 1 = role-split CTAs (gss_split.cuh)
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("GSS_SYNTH_SPLIT"); v = e ? atoi(e) : 0; }
+// tensor-memory variant (gss_tmem.cuh): per-thread streaming state parked in TMEM, 3 CTAs x 4 warps per SM
+template <int N, int HS, int ST>
+int launch_synth_tm(gss::SynthArgs a, cudaStream_t st) {
+    auto k = gss::mask_istft_tm_kernel<N, HS, ST>;
+    constexpr int WARPS_TM = gss::TmSmem<N>::WARPS;
+    const size_t smem = gss::TmSmem<N>::bytes();
+    if (int rc = prep(k, smem)) return rc;
+    if (int rc = ensure_tables<N>(st)) return rc;
+    a.ngroups = (a.S + ST - 1) / ST;
+    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS_TM, WARPS_TM, smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    int64_t items = a.B * a.ngroups * a.nchunk;
+    k<<<(unsigned)((items + WARPS_TM - 1) / WARPS_TM), WARPS_TM * 32, smem, st>>>(a);
+    return after_launch("mask_istft_tm_kernel");
+}
+int synth_variant() {       // 0 = one warp per pair (gss_stream.cuh), 1 = role-split CTAs (gss_split.cuh), 2 = tensor-memory state (gss_tmem.cuh)
+    int v = g_synth_variant.load(std::memory_order_relaxed);
+    if (v < 0) { const char* e = getenv("GSS_SYNTH_SPLIT"); v = e ? atoi(e) : 0; if (v < 0 || v > 2) v = 0; g_synth_variant.store(v); }
     return v;
 }
 
@@ -440,6 +458,7 @@ int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
             if (a.S == 1) return launch_synth_split<N, HS, 1>(a, st);
             return launch_synth_split<N, HS, 3>(a, st);
         }
+        if (synth_variant() == 2 && a.S % 3 == 0) return launch_synth_tm<N, HS, 3>(a, st);   // other S: default kernel
     }
     // sources carried per pass: 3 when S is a multiple of 3, else 2 (S even) or 1
     if (a.S % 3 == 0) return launch_synth<N, HS, 3>(a, st);
@@ -475,7 +494,24 @@ using namespace GSS_NS;
         return synth_by_s<NN, 4>(a, st);                                                                             \
     }
 #if GSS_HAS(1)
+#ifdef GSS_QUICK   // tuning builds only (tools/variant.sh): the C2 kernels alone, seconds instead of minutes to compile
+int stream512_stft_f32(int hs, bool lg, gss::StftArgs<float> a, cudaStream_t st) {
+    if (hs != 2) return fail(GSS_EUNSUPPORTED, "GSS_QUICK build: hop N/4 only");
+    return lg ? launch_stft<512, 2, true, float>(a, st) : launch_stft<512, 2, false, float>(a, st);
+}
+int stream512_stft_i16(int, bool, gss::StftArgs<int16_t>, cudaStream_t) { return fail(GSS_EUNSUPPORTED, "GSS_QUICK build"); }
+int stream512_istft(int hs, bool ex, gss::IstftArgs a, cudaStream_t st) {
+    if (hs != 2) return fail(GSS_EUNSUPPORTED, "GSS_QUICK build: hop N/4 only");
+    return ex ? launch_istft<512, 2, true>(a, st) : launch_istft<512, 2, false>(a, st);
+}
+int stream512_synth(int hs, gss::SynthArgs a, cudaStream_t st) {
+    if (hs != 2 || a.S != 3) return fail(GSS_EUNSUPPORTED, "GSS_QUICK build: hop N/4, S = 3 only");
+    if (synth_variant() == 2) return launch_synth_tm<512, 2, 3>(a, st);
+    return launch_synth<512, 2, 3>(a, st);
+}
+#else
 GSS_STREAM_PART(512)
+#endif
 #endif
 #if GSS_HAS(2)
 GSS_STREAM_PART(256)
@@ -579,6 +615,11 @@ int64_t gss_launch_count(void) { return g_launches.load(); }
 int gss_set_path(int path) {
     if (path < 0 || path > 2) return fail(GSS_EINVAL, "set_path: 0 = automatic, 1 = no register-exchange kernels, 2 = gss_generic.cuh only");
     g_force_generic.store(path);
+    return GSS_OK;
+}
+int gss_set_synth_variant(int variant) {
+    if (variant < 0 || variant > 2) return fail(GSS_EINVAL, "set_synth_variant: 0 = register-resident (default), 1 = role-split CTAs, 2 = tensor-memory state");
+    g_synth_variant.store(variant);
     return GSS_OK;
 }
 int gss_supported_fft_sizes(int* sizes, int cap) {

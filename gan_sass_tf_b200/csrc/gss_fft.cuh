@@ -319,8 +319,11 @@ __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
 
 // inverse (unnormalised, e^{+...}): a[k2] in the last-pass layout above
 //       -> a[n0] (lanes e=0,1: samples 2j+e + L*n0; re/im = the two real sequences).
-template <int N>
-__device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8]) {
+// `before_last` runs after the last exchange has been read and before the final butterflies: the place to start
+// loads whose latency the last pass hides (gss_tmem.cuh fetches the overlap-add state from tensor memory there).
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <int N, class Hook = NoHook>
+__device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8], Hook before_last = Hook()) {
     typedef Geo<N> G;
     const int j = c.j;
     team_sync(c);   // the previous transform's last read of the exchange buffers
@@ -381,6 +384,7 @@ __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8]) {
             a[k0] = cmul<true>(t, c.tw0[k0]);
         }
     }
+    before_last();
     dft8<true>(a);
 }
 

@@ -52,6 +52,13 @@ int64_t     gss_launch_count(void);
  * cross-checking the two implementations against each other. */
 int         gss_set_path(int path);
 
+/* Fused-synthesis kernel for FFT_SIZE 512 (gss_mask_istft): 0 = register-resident streaming kernel (default),
+ * 1 = role-split CTAs (analysis warp + one synthesis warp per source), 2 = per-thread state parked in tensor
+ * memory (S a multiple of 3; other S take the default).  All three give the same results; 1 and 2 are kept as
+ * measured design alternatives and cross-checks.  Process-wide; the environment variable GSS_SYNTH_SPLIT
+ * sets the initial value. */
+int         gss_set_synth_variant(int variant);
+
 /* FFT sizes this build has kernels for (writes up to `cap` entries, returns the count);
  * hops N/2 (the reference's SciPy default), N/4 and N/8 are supported for each. */
 int         gss_supported_fft_sizes(int* sizes, int cap);

@@ -249,6 +249,32 @@ def test_streaming_and_generic_paths_agree(T, ops):
             assert R.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6, f"path {path}"
 
 
+@pytest.mark.parametrize("H", [64, 128, 256])
+def test_synthesis_variants_agree(T, ops, H):
+    """The three N = 512 fused-synthesis kernels (register-resident, role-split CTAs, per-thread state parked in
+    tensor memory) against the oracle and against each other: ragged and odd lengths, several chunks per row."""
+    from gan_sass_tf_b200 import _native
+    N, S = 512, 3
+    rng = np.random.default_rng(500 + H)
+    for n, B in ((N, 1), (3 * N + 17, 2), (60 * N + 2 * H + 6, 3), (48000, 4)):
+        x = speechish(rng, B, n)
+        Tn, _ = R.frame_count(n, N, H)
+        mask = rng.random((B, S, Tn, N // 2)).astype(np.float32)
+        xd, md = dev(T, x), dev(T, mask)
+        ref = R.mask_istft_np(x, mask, N, H)
+        outs = []
+        for variant in (0, 1, 2):
+            try:
+                _native.set_synth_variant(variant)
+                outs.append(ops.mask_istft(xd, md, N, H).cpu().numpy())
+            finally:
+                _native.set_synth_variant(0)
+        for variant, o in enumerate(outs):
+            assert o.shape == outs[0].shape
+            assert R.rel_l2(o, outs[0]) < 2e-6, f"variant {variant}, n={n}"
+            assert R.rel_l2(o, np.asarray(ref, np.float64).reshape(o.shape)) < 1e-5, f"variant {variant} vs oracle, n={n}"
+
+
 @pytest.mark.parametrize("N,H", [(256, 32), (256, 64), (256, 128), (1024, 128), (1024, 256), (1024, 512),
                                  (2048, 256), (2048, 512), (2048, 1024), (4096, 512), (4096, 1024), (4096, 2048)])
 def test_team_kernels_all_sizes(T, ops, N, H):
