@@ -26,6 +26,9 @@
 #include <type_traits>
 #include "gss_fft.cuh"
 
+#ifndef GSS_STFT_MAXREG
+#define GSS_STFT_MAXREG 168           // 3 CTAs of 4 warps per SM
+#endif
 #ifndef GSS_ROLL_SOURCES
 #define GSS_ROLL_SOURCES 1
 #endif
@@ -51,6 +54,13 @@ struct SGeo {
 // periodic Hann (scipy.signal.get_window('hann', N)): 0.5 - 0.5 cos(2 pi i / N)
 template <int N>
 __device__ __forceinline__ float hann(int i) { return 0.5f - 0.5f * cospif(2.0f * (float)i / (float)N); }
+
+// read-only global load that stays where it is written (prefetches must not be moved down to their use)
+__device__ __forceinline__ float ldg_pinned(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // ---------------------------------------------------------------------------
 // sample access: the pair (p, p+1), p even, zero outside [0, n)
@@ -372,7 +382,7 @@ struct StftArgs {
 };
 
 template <int N, int HS, bool LOG, typename TIn, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 168 : ((65536 / (WARPS * 32)) / 8) * 8) stft_kernel(const StftArgs<TIn> p) {
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? GSS_STFT_MAXREG : ((65536 / (WARPS * 32)) / 8) * 8) stft_kernel(const StftArgs<TIn> p) {
     typedef SGeo<N, HS> SG; typedef Geo<N> G;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
@@ -531,23 +541,32 @@ __global__ void __launch_bounds__(WARPS * 32) istft_kernel(const IstftArgs p) {
     int64_t base = (int64_t)2 * qs * HS;
     const float* frow = p.feat + r * p.T * N;
 
-    for (int q = qs; q < q1; ++q) {
+    // features of the next pair are fetched one iteration ahead (volatile loads: the compiler would otherwise sink
+    // them past the transform's warp barriers down to their use and expose the whole DRAM latency every pair)
+    v2 nar[4], nai[4], nbr[4], nbi[4];
+    auto fetch = [&](int q) {
         const int64_t ta = 2 * (int64_t)q;
         const float* ra = frow + ta * N;
         const bool hb = ta + 1 < p.T;
-        v2 yar[4], yai[4], ybr[4], ybi[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int kx = ctx.cA + SG::L * i, ky = ctx.cB + SG::L * i;
-            yar[i] = make_float2(__ldg(ra + kx), __ldg(ra + ky));
-            yai[i] = make_float2(__ldg(ra + N / 2 + kx), __ldg(ra + N / 2 + ky));
+            nar[i] = make_float2(ldg_pinned(ra + kx), ldg_pinned(ra + ky));
+            nai[i] = make_float2(ldg_pinned(ra + N / 2 + kx), ldg_pinned(ra + N / 2 + ky));
             if (hb) {
-                ybr[i] = make_float2(__ldg(ra + N + kx), __ldg(ra + N + ky));
-                ybi[i] = make_float2(__ldg(ra + N + N / 2 + kx), __ldg(ra + N + N / 2 + ky));
+                nbr[i] = make_float2(ldg_pinned(ra + N + kx), ldg_pinned(ra + N + ky));
+                nbi[i] = make_float2(ldg_pinned(ra + N + N / 2 + kx), ldg_pinned(ra + N + N / 2 + ky));
             } else {
-                ybr[i] = make_float2(0.f, 0.f); ybi[i] = make_float2(0.f, 0.f);
+                nbr[i] = make_float2(0.f, 0.f); nbi[i] = make_float2(0.f, 0.f);
             }
         }
+    };
+    fetch(qs);
+    for (int q = qs; q < q1; ++q) {
+        v2 yar[4], yai[4], ybr[4], ybi[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { yar[i] = nar[i]; yai[i] = nai[i]; ybr[i] = nbr[i]; ybi[i] = nbi[i]; }
+        if (q + 1 < q1) fetch(q + 1);
         if (EXP) {
             v2 ea[4], eb[4];
             float mx = 0.f;

@@ -35,6 +35,12 @@ tag = os.path.basename(os.environ.get("GSS_LIB", "libgss.so"))
 extra = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("GSS_") and k != "GSS_LIB")
 t_st = timeit(lambda i: ops.stft_log(waves[i % 3], N, H)) if "--no-stft" not in sys.argv else float("nan")
 t_sy = timeit(lambda i: ops.mask_istft(waves[i % 3], masks[i % 3], N, H, out=out))
+if "--istft" in sys.argv:
+    feats = [ops.stft(w, N, H) for w in waves]
+    t_i = timeit(lambda i: ops.istft(feats[i % 3], H))
+    t_ie = timeit(lambda i: ops.istft(feats[i % 3], H, exp=True))
+    y = ops.istft(feats[0], H)
+    print(f"{tag:24s} istft {t_i:7.1f} us  istft_exp {t_ie:7.1f} us | fp {y.double().abs().sum().item():.6f}")
 ops.mask_istft(waves[0], masks[0], N, H, out=out)
 f = ops.stft_log(waves[0], N, H)
 print(f"{tag:24s} {extra:28s} stft_log {t_st:7.1f} us  mask_istft {t_sy:7.1f} us  | fp out {out.double().abs().sum().item():.6f} feat {f.double().abs().sum().item():.6f}")
