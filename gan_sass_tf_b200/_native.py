@@ -32,6 +32,8 @@ SIGNATURES = {
     "gss_istft_packed": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int64, _P]),
     "gss_mask_istft": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, _P, c_int64, _P]),
     "gss_apply_mask": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P]),
+    "gss_ola_norm_scale": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P]),
+    "gss_scale_packed": (c_int, [_P, _P, c_int64, c_int, c_float, c_float, _P]),
     "gss_to_log": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "gss_to_exp": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "gss_cross_snr": (c_int, [_P, _P, c_int64, c_int, c_int, c_int64, c_float, _P, _P]),

@@ -54,9 +54,16 @@ def _nh(fft_size, hop):
 def stft(wave, fft_size=None, hop=None, log=False):
     """``scipy.signal.stft(x, nperseg=N)[2]`` + ``utils.spectrum_to_feature``
     (main.py:97-98) for a batch: ``wave [..., n]`` (float32 or int16) ->
-    packed feature ``[..., T, N]`` float32.  ``log=True`` fuses ``to_log_signal``."""
+    packed feature ``[..., T, N]`` float32.  ``log=True`` fuses ``to_log_signal``.
+    Differentiable in ``wave`` (adjoint = scaled overlap-add iSTFT, ``_stft_adjoint``)."""
     _dev(wave, "stft")
     N, H = _nh(fft_size, hop)
+    if torch.is_grad_enabled() and wave.requires_grad:
+        return _Stft.apply(wave, N, H, bool(log))
+    return _stft_fwd(wave, N, H, log)
+
+
+def _stft_fwd(wave, N, H, log=False):
     if wave.dtype == torch.int16:
         w, fn = wave.contiguous(), _n.lib().gss_stft_packed_i16
     else:
@@ -82,11 +89,21 @@ def istft(feature, hop=None, length=None, exp=False):
     """``utils.feature_to_spectrum`` + ``scipy.signal.istft(Z, nperseg=N)``
     (main.py:110-111): ``feature [..., T, N]`` -> ``[..., (T-1)*H]``.  ``exp=True``
     applies ``to_exp_signal`` first (main.py:342).  ``length`` trims the tail
-    (SciPy itself returns the ``nadd`` padding samples, K4)."""
+    (SciPy itself returns the ``nadd`` padding samples, K4).  Differentiable in ``feature``
+    (adjoint = scaled STFT of the normalised gradient, ``_istft_adjoint``)."""
+    _dev(feature, "istft")
+    assert feature.dim() >= 2, "istft: feature must be [..., T, N]"
+    N, H = _nh(feature.shape[-1], hop)
+    if torch.is_grad_enabled() and feature.requires_grad:
+        out = _Istft.apply(feature, H, bool(exp))
+    else:
+        out = _istft_fwd(feature, H, exp)
+    return out if length is None else out[..., :length]
+
+
+def _istft_fwd(feature, H, exp=False):
     f = _f32c(feature, "istft")
-    assert f.dim() >= 2, "istft: feature must be [..., T, N]"
     T, N = f.shape[-2], f.shape[-1]
-    N, H = _nh(N, hop)
     lead = f.shape[:-2]
     R = 1
     for d in lead:
@@ -96,7 +113,92 @@ def istft(feature, hop=None, length=None, exp=False):
     with torch.cuda.device(f.device):
         _n.check(_n.lib().gss_istft_packed(f.data_ptr(), R, T, N, H, _n.FLAG_EXP if exp else 0, hparams.EPS,
                                            out.data_ptr(), L, _stream()))
-    return out if length is None else out[..., :length]
+    return out
+
+
+# adjoints of the two transforms: each is the OTHER transform's kernel between two scalings
+def _scale_packed(f, c_all, c_edge):
+    N = f.shape[-1]
+    out = torch.empty_like(f)
+    with torch.cuda.device(f.device):
+        _n.check(_n.lib().gss_scale_packed(f.data_ptr(), out.data_ptr(), f.numel() // N, N, c_all, c_edge, _stream()))
+    return out
+
+
+def _ola_norm_scale(x, length, T, N, H, inverse, scale):
+    """x [R, ld] (first ``length`` samples of a row used) -> [R, length] times or over the overlap-add weight"""
+    R, ld = x.shape
+    out = torch.empty((R, length), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _n.check(_n.lib().gss_ola_norm_scale(x.data_ptr(), out.data_ptr(), R, length, ld, length, T, N, H,
+                                             1 if inverse else 0, scale, _stream()))
+    return out
+
+
+def _istft_adjoint(g, T, N, H):
+    """g = dL/d(wave) ``[R, (T-1)H]`` -> dL/d(feature) ``[R, T, N]``: (N/2) STFT(g / norm), DC and Nyquist halved"""
+    g = _f32c(g, "istft.backward")
+    L = (T - 1) * H
+    assert g.dim() == 2 and g.shape[1] == L
+    u = _ola_norm_scale(g, L, T, N, H, True, 1.0)
+    G = _stft_fwd(u, N, H)
+    assert G.shape[-2] == T
+    return _scale_packed(G, 0.5 * N, 0.5)
+
+
+def _stft_adjoint(g, n, N, H):
+    """g = dL/d(feature) ``[B, T, N]`` -> dL/d(wave) ``[B, n]``: (4/N) norm * iSTFT(g with interior bins halved)"""
+    g = _f32c(g, "stft.backward")
+    T = g.shape[-2]
+    y = _istft_fwd(_scale_packed(g, 0.5, 2.0), H)               # [B, (T-1)H], already divided by norm
+    return _ola_norm_scale(y, n, T, N, H, False, 4.0 / N)
+
+
+def _logexp_bwd_n(x, gout, fn_name, N):
+    g = _f32c(gout, fn_name)
+    gin = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _n.check(getattr(_n.lib(), fn_name)(x.data_ptr(), g.data_ptr(), gin.data_ptr(), x.numel() // N, N, hparams.EPS, _stream()))
+    return gin
+
+
+class _Stft(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wave, N, H, log):
+        w = _f32c(wave, "stft")
+        ctx.save_for_backward(w)
+        ctx.cfg = (N, H, log)
+        return _stft_fwd(w, N, H, log)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (w,) = ctx.saved_tensors
+        N, H, log = ctx.cfg
+        n = w.shape[-1]
+        g = _f32c(gout, "stft.backward").reshape(-1, gout.shape[-2], N)
+        if log:     # chain through to_log_signal: needs the uncompressed features, recomputed (one STFT launch)
+            raw = _stft_fwd(w.reshape(-1, n), N, H, False)
+            g = _logexp_bwd_n(raw, g, "gss_to_log_bwd", N)
+        return _stft_adjoint(g, n, N, H).reshape(w.shape), None, None, None
+
+
+class _Istft(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feature, H, exp):
+        f = _f32c(feature, "istft")
+        ctx.save_for_backward(f if exp else f.new_empty(0))
+        ctx.cfg = (H, exp, f.shape)
+        return _istft_fwd(f, H, exp)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (f,) = ctx.saved_tensors
+        H, exp, shape = ctx.cfg
+        T, N = shape[-2], shape[-1]
+        g = _istft_adjoint(gout.reshape(-1, gout.shape[-1]), T, N, H)
+        if exp:
+            g = _logexp_bwd_n(f.reshape(-1, T, N), g, "gss_to_exp_bwd", N)
+        return g.reshape(shape), None, None
 
 
 class _ApplyMask(torch.autograd.Function):
@@ -146,11 +248,46 @@ def _apply_mask_fwd(mix_feature, mask):
 
 def mask_istft(wave, mask, fft_size=None, hop=None, out=None):
     """Fused synthesis: STFT of the mixture (recomputed from ``wave [B,n]``), per-source
-    mask ``[B,S,T,N/2]``, inverse STFT with overlap-add -> ``[B*S, (T-1)*H]``."""
+    mask ``[B,S,T,N/2]``, inverse STFT with overlap-add -> ``[B*S, (T-1)*H]``.  Differentiable in
+    ``mask`` and ``wave`` (iSTFT adjoint -> ``gss_apply_mask_bwd`` -> STFT adjoint): a mask separator can be
+    trained against a waveform-domain loss through the native kernels."""
+    _dev(wave, "mask_istft"); _dev(mask, "mask_istft")
+    assert wave.dim() == 2 and mask.dim() == 4, "mask_istft: wave [B,n], mask [B,S,T,N/2]"
+    N, H = _nh(fft_size if fft_size is not None else 2 * mask.shape[-1], hop)
+    if torch.is_grad_enabled() and (wave.requires_grad or mask.requires_grad):
+        assert out is None, "mask_istft: out= is not supported when gradients are required"
+        return _MaskIstft.apply(wave, mask, N, H)
+    return _mask_istft_fwd(wave, mask, N, H, out)
+
+
+class _MaskIstft(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wave, mask, N, H):
+        w, m = _f32c(wave, "mask_istft"), _f32c(mask, "mask_istft")
+        ctx.save_for_backward(w, m)
+        ctx.cfg = (N, H)
+        return _mask_istft_fwd(w, m, N, H, None)
+
+    @staticmethod
+    def backward(ctx, gout):
+        w, m = ctx.saved_tensors
+        N, H = ctx.cfg
+        B, S, T = m.shape[0], m.shape[1], m.shape[2]
+        gy = _istft_adjoint(gout, T, N, H)                      # [B*S, T, N]
+        x = _stft_fwd(w, N, H)                                  # mixture spectrum, recomputed as in the forward
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gm = torch.empty_like(m) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(x.device):
+            _n.check(_n.lib().gss_apply_mask_bwd(x.data_ptr(), m.data_ptr(), gy.data_ptr(), B, S, T, N,
+                                                 gx.data_ptr() if gx is not None else None,
+                                                 gm.data_ptr() if gm is not None else None, _stream()))
+        gw = _stft_adjoint(gx, w.shape[-1], N, H) if gx is not None else None
+        return gw, gm, None, None
+
+
+def _mask_istft_fwd(wave, mask, N, H, out=None):
     w = _f32c(wave, "mask_istft")
     m = _f32c(mask, "mask_istft")
-    assert w.dim() == 2 and m.dim() == 4, "mask_istft: wave [B,n], mask [B,S,T,N/2]"
-    N, H = _nh(fft_size if fft_size is not None else 2 * m.shape[-1], hop)
     B, n = w.shape
     S = m.shape[1]
     T, _ = _n.frame_count(n, N, H)

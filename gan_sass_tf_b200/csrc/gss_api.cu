@@ -709,6 +709,31 @@ int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_
     return after_launch("apply_mask_kernel");
 }
 
+int gss_ola_norm_scale(const float* in, float* out, int64_t rows, int64_t len, int64_t ld_in, int64_t ld_out, int64_t T, int N, int H,
+                       int inverse, float scale, void* stream) {
+    int hs = 0;
+    if (int rc = check_nh(N, H, &hs)) return rc;
+    if (!in || !out) return fail(GSS_EINVAL, "ola_norm_scale: null pointer");
+    if (rows < 0 || len < 0 || ld_in < len || ld_out < len || T < 1) return fail(GSS_EINVAL, "ola_norm_scale: bad shape");
+    if (len > (T - 1) * (int64_t)H) return fail(GSS_EINVAL, "ola_norm_scale: len=%lld exceeds the iSTFT length (T-1)*H=%lld", (long long)len, (long long)((T - 1) * (int64_t)H));
+    int64_t total = rows * len;
+    if (total == 0) return GSS_OK;
+    if (inverse) gss::ola_norm_scale_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, len, ld_in, ld_out, T, N, H, scale);
+    else gss::ola_norm_scale_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, len, ld_in, ld_out, T, N, H, scale);
+    return after_launch("ola_norm_scale_kernel");
+}
+
+int gss_scale_packed(const float* in, float* out, int64_t rows, int N, float c_all, float c_edge, void* stream) {
+    if (!in || !out) return fail(GSS_EINVAL, "scale_packed: null pointer");
+    if (N < 8 || N % 8) return fail(GSS_EINVAL, "scale_packed: N=%d must be a multiple of 8", N);
+    if (rows < 0) return fail(GSS_EINVAL, "scale_packed: rows < 0");
+    if (((uintptr_t)in | (uintptr_t)out) & 15) return fail(GSS_EINVAL, "scale_packed: buffers must be 16-byte aligned");
+    int64_t total = rows * (N / 4);
+    if (total == 0) return GSS_OK;
+    gss::scale_packed_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, N, c_all, c_edge);
+    return after_launch("scale_packed_kernel");
+}
+
 static int logexp(bool ex, const float* in, float* out, int64_t rows, int N, float eps, void* stream) {
     if (!in || !out) return fail(GSS_EINVAL, "to_log/to_exp: null pointer");
     if (N < 8 || N % 8) return fail(GSS_EINVAL, "to_log/to_exp: N=%d must be a multiple of 8", N);

@@ -47,6 +47,44 @@ __global__ void __launch_bounds__(256) apply_mask_kernel(const float* __restrict
     }
 }
 
+// Overlap-add weight of scipy.signal.istft at sample p of the trimmed output: norm[p] = sum over the frames t in
+// [0, T) that cover it of hann[p + N/2 - t*H]^2, with SciPy's guard (norm > 1e-10, else 1).  out = in / norm
+// (INV) or in * norm, times `scale`.  Used by the adjoints of the transforms: d iSTFT^T = (N/2) STFT(g / norm),
+// d STFT^T = (4/N) norm * iSTFT(g').
+template <bool INV>
+__global__ void __launch_bounds__(256) ola_norm_scale_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows,
+                                                             int64_t len, int64_t ld_in, int64_t ld_out, int64_t T, int N, int H, float scale) {
+    const int64_t total = rows * len;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / len, p = i - r * len;
+        const int64_t pp = p + N / 2;
+        int64_t tlo = pp - (N - 1); tlo = tlo <= 0 ? 0 : (tlo + H - 1) / H;
+        int64_t thi = pp / H; if (thi > T - 1) thi = T - 1;
+        float nrm = 0.f;
+        for (int64_t t = tlo; t <= thi; ++t) {
+            const float w = 0.5f - 0.5f * cospif(2.0f * (float)(pp - t * H) / (float)N);
+            nrm = fmaf(w, w, nrm);
+        }
+        nrm = nrm > 1e-10f ? nrm : 1.0f;
+        const float v = __ldg(in + r * ld_in + p);
+        out[r * ld_out + p] = scale * (INV ? v / nrm : v * nrm);
+    }
+}
+
+// packed features: every slot times c_all, the DC slot (0) and the Nyquist slot (N/2) times c_edge in addition
+__global__ void __launch_bounds__(256) scale_packed_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int N,
+                                                           float c_all, float c_edge) {
+    const int q = N / 4;
+    const int64_t total = rows * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k4 = (int)(i % q);
+        float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+        v.x *= c_all; v.y *= c_all; v.z *= c_all; v.w *= c_all;
+        if (k4 == 0 || k4 == q / 2) v.x *= c_edge;
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

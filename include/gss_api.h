@@ -97,6 +97,16 @@ int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64
 int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_t T, int N,
                    float* out, void* stream);
 
+/* Building blocks of the transforms' adjoints (the reference never differentiates through its SciPy
+ * calls, main.py:97/111, so these have no reference counterpart).  With norm[p] = sum_t hann^2 over the frames that
+ * cover sample p - the overlap-add weight scipy.signal.istft divides by, including its > 1e-10 guard -
+ *   out[r, p] = scale * in[r, p] / norm[p]   (inverse != 0)      or      scale * in[r, p] * norm[p],   p < len <= (T-1)*H;
+ * gss_scale_packed multiplies packed features by c_all and their DC / Nyquist slots (0 and N/2) by c_edge on top.
+ *   d iSTFT^T (g) = scale_packed(STFT(g / norm), N/2, 1/2)       d STFT^T (g) = (4/N) * norm * iSTFT(scale_packed(g, 1/2, 2)) */
+int gss_ola_norm_scale(const float* in, float* out, int64_t rows, int64_t len, int64_t ld_in, int64_t ld_out,
+                       int64_t T, int N, int H, int inverse, float scale, void* stream);
+int gss_scale_packed(const float* in, float* out, int64_t rows, int N, float c_all, float c_edge, void* stream);
+
 /* A3 / A5: ops.to_log_signal / ops.to_exp_signal (app/ops.py:228-251) on `rows` rows of N */
 int gss_to_log(const float* in, float* out, int64_t rows, int N, float eps, void* stream);
 int gss_to_exp(const float* in, float* out, int64_t rows, int N, float eps, void* stream);

@@ -110,6 +110,123 @@ def test_apply_mask_backward_matches_autograd(T, ops):
     assert R.rel_l2(mask.grad.cpu().numpy(), kd.grad.cpu().numpy()) < 1e-6
 
 
+# ---- adjoints of the transforms (optional part) -----------------------
+def _t_window(T, N):
+    return 0.5 - 0.5 * T.cos(2 * np.pi * T.arange(N, dtype=T.float64, device="cuda") / N)
+
+
+def _torch_stft_feature(T, x, N, H):
+    """float64, differentiable restatement of oracle.stft_feature_np (scipy.signal.stft defaults + packing)"""
+    n = x.shape[-1]
+    nadd = (-n % H) % N
+    xp = T.nn.functional.pad(x, (N // 2, N // 2 + nadd))
+    Z = T.fft.rfft(xp.unfold(-1, N, H) * _t_window(T, N), dim=-1) * (2.0 / N)
+    return T.cat([Z.real[..., :N // 2], Z.real[..., N // 2:], Z.imag[..., 1:N // 2]], dim=-1)
+
+
+def _torch_istft_feature(T, f, H):
+    """float64, differentiable restatement of oracle.istft_feature_np (scipy.signal.istft defaults)"""
+    N, Tn = f.shape[-1], f.shape[-2]
+    zero = T.zeros_like(f[..., :1])
+    Z = T.complex(T.cat([f[..., :N // 2], f[..., N // 2:N // 2 + 1]], -1), T.cat([zero, f[..., N // 2 + 1:], zero], -1))
+    w = _t_window(T, N)
+    y = T.fft.irfft(Z, n=N, dim=-1) * (N / 2) * w
+    total = N + (Tn - 1) * H
+    acc = T.zeros(f.shape[:-2] + (total,), dtype=T.float64, device=f.device)
+    nrm = T.zeros(total, dtype=T.float64, device=f.device)
+    for t in range(Tn):
+        acc = acc + T.nn.functional.pad(y[..., t, :], (t * H, total - N - t * H))
+        nrm[t * H:t * H + N] += w * w
+    nrm = T.where(nrm > 1e-10, nrm, T.ones_like(nrm))
+    return (acc / nrm)[..., N // 2:total - N // 2]
+
+
+@pytest.mark.parametrize("N,H", [(512, 128), (256, 128), (256, 32), (1024, 256), (64, 16)])
+@pytest.mark.parametrize("log", [False, True])
+def test_stft_backward_matches_autograd(T, ops, hp, N, H, log):
+    g = T.Generator(device="cuda").manual_seed(N + H)
+    n = 5 * N + 3 * H + 7
+    x = (T.randn(2, n, device="cuda", generator=g) * 0.2).requires_grad_(True)
+    y = ops.stft(x, N, H, log=log)
+    go = T.randn(y.shape, device="cuda", generator=g)
+    y.backward(go)
+    xd = x.detach().double().requires_grad_(True)
+    yr = _torch_stft_feature(T, xd, N, H)
+    if log:
+        yr = _torch_log(yr, hp.EPS)
+    yr.backward(go.double())
+    assert R.rel_l2(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < REL_L2
+    assert R.rel_l2(x.grad.cpu().numpy(), xd.grad.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("N,H", [(512, 128), (256, 128), (256, 32), (1024, 256), (64, 16)])
+@pytest.mark.parametrize("exp", [False, True])
+def test_istft_backward_matches_autograd(T, ops, hp, N, H, exp):
+    g = T.Generator(device="cuda").manual_seed(N + H + 1)
+    Tn = 5 * N // H + 4
+    f = (T.randn(3, Tn, N, device="cuda", generator=g) * 0.3).requires_grad_(True)
+    y = ops.istft(f, H, exp=exp, length=(Tn - 1) * H - 5)          # the trimmed tail gets a zero gradient
+    go = T.randn(y.shape, device="cuda", generator=g)
+    y.backward(go)
+    fd = f.detach().double().requires_grad_(True)
+    yr = _torch_istft_feature(T, _torch_exp(fd, hp.EPS) if exp else fd, H)[..., :(Tn - 1) * H - 5]
+    yr.backward(go.double())
+    assert R.rel_l2(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < REL_L2
+    assert R.rel_l2(f.grad.cpu().numpy(), fd.grad.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("N,H", [(512, 128), (512, 256), (256, 64), (1024, 256)])
+def test_mask_istft_backward_matches_autograd(T, ops, N, H):
+    """a waveform-domain loss back-propagated to the masks (what trains a mask separator) and to the mixture"""
+    g = T.Generator(device="cuda").manual_seed(N + H + 2)
+    B, S, n = 2, 3, 6 * N + H + 3
+    Tn, _ = R.frame_count(n, N, H)
+    x = (T.randn(B, n, device="cuda", generator=g) * 0.2).requires_grad_(True)
+    m = T.rand(B, S, Tn, N // 2, device="cuda", generator=g).requires_grad_(True)
+    y = ops.mask_istft(x, m, N, H)
+    go = T.randn(y.shape, device="cuda", generator=g)
+    y.backward(go)
+    xd, md = x.detach().double().requires_grad_(True), m.detach().double().requires_grad_(True)
+    feat = _torch_stft_feature(T, xd, N, H)
+    masked = (T.cat([md, md], dim=-1) * feat[:, None]).reshape(B * S, Tn, N)
+    yr = _torch_istft_feature(T, masked, H)
+    yr.backward(go.double())
+    assert R.rel_l2(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < REL_L2
+    assert R.rel_l2(m.grad.cpu().numpy(), md.grad.cpu().numpy()) < 2e-5
+    assert R.rel_l2(x.grad.cpu().numpy(), xd.grad.cpu().numpy()) < 2e-5
+
+
+def test_mask_separator_trains_through_native_kernels(T, ops, hp):
+    """The plugin surface end to end with gradients: waveforms -> stft_log -> registered mask separator ->
+    mask_istft -> waveform-domain loss -> Adam.  Two sources in disjoint bands are separable by a per-bin mask,
+    so a few steps through the native forward and adjoint kernels must cut the loss substantially."""
+    from gan_sass_tf_b200.app import modules  # noqa: F401  (registers 'toy-mask')
+    hp.FFT_SIZE, hp.HOP_SIZE, hp.MAX_N_SIGNAL = 256, 64, 1
+    N, H, S, B, n = 256, 64, 2, 8, 4096
+    hp.SEPARATOR_TYPE = 'toy-mask'
+    sep = hp.get_separator()(None, 'train_test_sep')
+    g = T.Generator(device="cuda").manual_seed(21)
+    t = T.arange(n, device="cuda", dtype=T.float32) / 16000.0
+    lo = T.sin(2 * np.pi * 500.0 * t)[None] * (0.2 + 0.1 * T.rand(B, 1, device="cuda", generator=g))
+    hi = T.sin(2 * np.pi * 5000.0 * t)[None] * (0.2 + 0.1 * T.rand(B, 1, device="cuda", generator=g))
+    target = T.stack([lo, hi], dim=1).reshape(B * S, n)
+    mix = lo + hi
+    logf = ops.stft_log(mix, N, H)
+    sep(logf)                                            # creates the lazily-built layers
+    opt = T.optim.Adam(list(sep.p.parameters()), lr=3e-3)
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        masks = sep(logf)                                # [B, S, T, N/2], differentiable torch module
+        est = ops.mask_istft(mix, masks, N, H)[:, :n]    # native forward, native adjoint
+        loss = ((est - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(p.grad is not None and T.isfinite(p.grad).all() for p in sep.p.parameters())
+    assert losses[-1] < 0.25 * losses[0], losses
+
+
 # ---- demo-mode edges --------------------------------------------------------------
 @pytest.mark.parametrize("n,num", [(1000, 363), (1001, 364), (44100, 16000), (8000, 16000), (8001, 16001), (999, 500), (500, 1001)])
 def test_resample_matches_scipy(T, ops, n, num):
