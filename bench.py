@@ -179,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -376,14 +376,35 @@ def run_native(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_serial_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 (NCCL prints its version
+    banner there at the first collective, libraries print warnings) is sent to stderr for the whole run."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
