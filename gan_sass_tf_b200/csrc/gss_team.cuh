@@ -296,6 +296,13 @@ struct Ola {
         }
         return s > 1e-10f ? s : 1.0f;     // scipy.signal.istft: where(norm > 1e-10, norm, 1)
     }
+    // all ADV slots starting at `base` are inside the output and covered by R frames: plain scaled stores
+    __device__ __forceinline__ bool interior(int64_t base) const {
+        return base >= G::FS - G::HS && base >= G::FS / 2 && base + G::ADV <= (T - 1) * G::HS + (G::HS < G::FS / 2 ? G::HS : G::FS / 2);
+    }
+    __device__ __forceinline__ void write_fast(float* row, int64_t sl, int m, float v) const {
+        row[(sl - G::FS / 2) * G::SLOT + t] = v * (G::CONST_NORM ? oscale : invn[m]);
+    }
     __device__ __forceinline__ void write(float* row, int64_t sl, int m, float v) const {
         v *= G::CONST_NORM ? oscale : invn[m];
         if (sl < G::FS / 2 || sl >= G::FS / 2 + (T - 1) * G::HS) return;
@@ -464,8 +471,13 @@ __global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_ISTFT) istft_k
         for (int i = 0; i < G::RS; ++i) cur[i] = i < G::KEEP ? acc[i] : 0.f;
         ola_accumulate<G>(v, win, cur);
         if (q >= q0) {
+            if (o.interior(base)) {
 #pragma unroll
-            for (int i = 0; i < G::ADV; ++i) o.write(orow, base + i, i % HS, cur[i]);
+                for (int i = 0; i < G::ADV; ++i) o.write_fast(orow, base + i, i % HS, cur[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < G::ADV; ++i) o.write(orow, base + i, i % HS, cur[i]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < G::KEEP; ++i) acc[i] = cur[i + G::ADV];
@@ -533,6 +545,7 @@ __global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_SYNTH) mask_is
         const int64_t ta = 2 * (int64_t)q;
         const bool hb = ta + 1 < p.T;
         const bool own = q >= q0;
+        const bool fast = o.interior(base);
         // gains of source s for this thread's bins, fetched one source ahead of their use
         constexpr int KI = NH / G::TPT;                           // bins k = t + i*TPT, plus k = N/2 (gain 0 again)
         float ga[KI], gb[KI], ga_n[KI], gb_n[KI];
@@ -567,8 +580,13 @@ __global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_SYNTH) mask_is
                 ola_accumulate<G>(v, win, cur);
                 if (own) {
                     float* orow = orow0 + s * p.ld_out;
+                    if (fast) {
 #pragma unroll
-                    for (int i = 0; i < G::ADV; ++i) o.write(orow, base + i, i % HS, cur[i]);
+                        for (int i = 0; i < G::ADV; ++i) o.write_fast(orow, base + i, i % HS, cur[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < G::ADV; ++i) o.write(orow, base + i, i % HS, cur[i]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < G::KEEP; ++i) acc[s][i] = cur[i + G::ADV];
