@@ -103,7 +103,7 @@ def supported_fft_sizes():
 
 
 def set_path(path: int):
-    """0 = automatic kernel selection, 1 = any-size shared-memory kernels only."""
+    """0 = automatic kernel selection, 1 = no register-exchange kernels (team kernels), 2 = per-frame kernels only."""
     check(lib().gss_set_path(path))
 
 

@@ -8,7 +8,7 @@
  * reference would add.
  *
  * Conventions
- *   - N  = FFT_SIZE (app/hparams.py:12), power of two in [256, 1024] this round;
+ *   - N  = FFT_SIZE (app/hparams.py:12), power of two in [64, 4096] (gss_supported_fft_sizes);
  *     H  = hop, one of N/2 (the reference's SciPy default), N/4, N/8.
  *   - "packed feature" = the reference's [T, N] float32 layout of app/utils.py:8-26:
  *     feat[t,k]=Re X[k] (0<=k<N/2), feat[t,N/2]=Re X[N/2], feat[t,N/2+k]=Im X[k].
@@ -47,9 +47,10 @@ const char* gss_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t     gss_launch_count(void);
 
-/* Kernel selection: 0 = automatic (register-streaming kernels where the FFT size has them, the
- * any-size shared-memory kernels otherwise), 1 = any-size kernels only.  Process-wide; meant for
- * cross-checking the two implementations against each other. */
+/* Kernel selection: 0 = automatic (register-exchange streaming kernels for N = 256 / 512, shared-memory team
+ * kernels for 1024 / 2048 / 4096, per-frame kernels for 64 / 128), 1 = no register-exchange kernels (team kernels
+ * take 256 / 512 too), 2 = per-frame kernels only.  Process-wide; meant for cross-checking the implementations
+ * against each other. */
 int         gss_set_path(int path);
 
 /* Fused-synthesis kernel for FFT_SIZE 512 (gss_mask_istft): 0 = register-resident streaming kernel (default),
