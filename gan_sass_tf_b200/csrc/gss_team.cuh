@@ -537,28 +537,34 @@ __global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_SYNTH) mask_is
     float ring[G::RS];
     load_slots<G, G::RS>(row, p.n, base, t, ring);
 
+    // gains of one source for this thread's bins (k = t + i*TPT, plus k = N/2 which shares gain 0), fetched one source
+    // ahead of their use - across pairs too: source 0 of the next pair is requested while the last source of this one
+    // is transformed, so no pair starts by waiting for DRAM
+    constexpr int KI = NH / G::TPT;
+    auto fetch = [&](int q_, int s, float (&a)[KI], float (&bq)[KI]) {
+        const int64_t ta_ = 2 * (int64_t)q_;
+        const bool hb_ = ta_ + 1 < p.T;
+        const float* ma = mrow0 + s * msrc + ta_ * NH + t;
+#pragma unroll
+        for (int i = 0; i < KI; ++i) { a[i] = ldg_here(ma + i * G::TPT); bq[i] = hb_ ? ldg_here(ma + NH + i * G::TPT) : 0.f; }
+    };
+    float ga[KI], gb[KI], ga_n[KI], gb_n[KI];
+    fetch(qs, 0, ga_n, gb_n);
+
     for (int q = qs; q < q1; ++q) {
         forward_from_ring<G>(ring, win, X, Y, tw, t);
 #pragma unroll
         for (int i = 0; i < G::KEEP; ++i) ring[i] = ring[i + G::ADV];
         if (q + 1 < q1) load_slots<G, G::ADV>(row, p.n, base + G::RS, t, &ring[G::KEEP]);
-        const int64_t ta = 2 * (int64_t)q;
-        const bool hb = ta + 1 < p.T;
         const bool own = q >= q0;
         const bool fast = o.interior(base);
-        // gains of source s for this thread's bins, fetched one source ahead of their use
-        constexpr int KI = NH / G::TPT;                           // bins k = t + i*TPT, plus k = N/2 (gain 0 again)
-        float ga[KI], gb[KI], ga_n[KI], gb_n[KI];
-        auto fetch = [&](int s, float (&a)[KI], float (&bq)[KI]) {
-            const float* ma = mrow0 + s * msrc + ta * NH + t;
 #pragma unroll
-            for (int i = 0; i < KI; ++i) { a[i] = ldg_here(ma + i * G::TPT); bq[i] = hb ? ldg_here(ma + NH + i * G::TPT) : 0.f; }
-        };
-        fetch(0, ga, gb);
+        for (int i = 0; i < KI; ++i) { ga[i] = ga_n[i]; gb[i] = gb_n[i]; }
 #pragma unroll
         for (int s = 0; s < ST; ++s) {
             if (s < ns) {
-                if (s + 1 < ns) fetch(s + 1, ga_n, gb_n);
+                if (s + 1 < ns) fetch(q, s + 1, ga_n, gb_n);
+                else if (q + 1 < q1) fetch(q + 1, 0, ga_n, gb_n);
 #pragma unroll
                 for (int i = 0; i < KI; ++i) {
                     const int k = t + i * G::TPT;
