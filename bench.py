@@ -358,6 +358,9 @@ def run_native(args):
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "bytes_per_launch": synth_b, "ms_per_launch": synth_ms,
+                         "limiter": "not HBM at this batch: issue cadence of the SM sub-partitions (half-rate FP32x2 + shared-memory "
+                                    "instructions; static schedule 3779 cycles per frame pair and warp = 172 us per launch), "
+                                    "DESIGN.md 4.5 / profiles/r1c_tmem_variant.txt",
                          "step_frac_of_hbm": (stft_b + synth_b) / (total_ms / args.steps * 1e-3) / 1e9 / peak,
                          "stft_kernel": {"bytes_per_launch": stft_b, "ms_per_launch": stft_ms,
                                          "achieved": stft_b / (stft_ms * 1e-3) / 1e9}},
