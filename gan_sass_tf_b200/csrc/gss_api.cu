@@ -435,9 +435,15 @@ int launch_synth_tm(gss::SynthArgs a, cudaStream_t st) {
     constexpr int WARPS_TM = gss::TmSmem<N>::WARPS;
     const size_t smem = gss::TmSmem<N>::bytes();
     if (int rc = prep(k, smem)) return rc;
+    // three CTAs need 206 KB of shared memory per SM: ask for the largest carve-out (the default heuristic left one CTA per SM resident)
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     if (int rc = ensure_tables<N>(st)) return rc;
     a.ngroups = (a.S + ST - 1) / ST;
-    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS_TM, WARPS_TM, smem));
+    // resident slots from the launch bounds the kernel is compiled for (the occupancy query under-reports this kernel)
+    int64_t slots = team_slots(k, WARPS_TM, WARPS_TM, smem);
+    const int64_t by_bounds = (int64_t)sm_count() * GSS_TM_MINB * WARPS_TM;
+    if (slots < by_bounds) slots = by_bounds;
+    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, slots);
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.B * a.ngroups * a.nchunk;
     k<<<(unsigned)((items + WARPS_TM - 1) / WARPS_TM), WARPS_TM * 32, smem, st>>>(a);

@@ -22,11 +22,11 @@
 // the last butterfly pass hides its latency; because accumulator sets are addressed by a run-time column the
 // source loop needs neither unrolling nor register rotation.
 //
-// Outcome (B200, C2, profiles/r1c_tmem_variant.txt): bit-compatible results, 273 us at 12 warps per SM against
-// 188 us of the register-resident kernel at 8; the same kernel held to 2 CTAs per SM runs 256 us, with every
-// TMEM access stubbed out 245 us.  Tensor-memory traffic itself costs ~4 %; going from 8 to 12 resident warps
-// buys nothing.  Together with the other occupancy experiments this is what pins the fused
-// synthesis on the SM sub-partitions' issue ports rather than on latency hiding.
+// Outcome (B200, C2, profiles/r1c_tmem_variant.txt): bit-compatible results, 201 us at 9.3 resident warps per SM (ncu)
+// against 188 us of the register-resident kernel at 7.2 and 189 us of the role-split kernel at 10.8.  Tensor-memory
+// traffic itself costs ~4 %, the finer mask staging ~15 % (bisected at equal occupancy); the extra resident warps buy
+// nothing back.  Together with the other occupancy experiments this is what pins the fused synthesis
+// on the SM sub-partitions' issue cadence rather than on latency hiding.
 #pragma once
 #include "gss_stream.cuh"
 

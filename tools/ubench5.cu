@@ -93,5 +93,11 @@ void run(int ctas_per_sm, const char* name) {
 int main() {
     for (int c = 1; c <= 3; ++c) { run<128, 0>(c, "st+ld"); run<128, 1>(c, "ld"); run<128, 2>(c, "st"); }
     run<256, 0>(2, "st+ld"); run<128, 0>(4, "st+ld"); run<128, 1>(4, "ld");
+    // residency map: kernel time for c CTAs per SM (fixed work per CTA) by allocation size
+    for (int c = 1; c <= 6; ++c) { run<32, 0>(c, "map32"); }
+    for (int c = 1; c <= 6; ++c) { run<64, 0>(c, "map64"); }
+    for (int c = 1; c <= 4; ++c) { run<128, 0>(c, "map128"); }
+    for (int c = 1; c <= 3; ++c) { run<256, 0>(c, "map256"); }
+    for (int c = 1; c <= 2; ++c) { run<512, 0>(c, "map512"); }
     return 0;
 }
