@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GSS_LIB") or os.path.join(_HERE, "lib", "libgss.so")
 
 GSS_OK, GSS_EINVAL, GSS_EUNSUPPORTED, GSS_ECUDA, GSS_ENOMEM = 0, -1, -2, -3, -4
-FLAG_LOG, FLAG_EXP = 1, 2
+FLAG_LOG, FLAG_EXP, FLAG_REVERSE = 1, 2, 4
 
 # name -> (restype, argtypes); mirrors include/gss_api.h one to one
 _P = c_void_p
@@ -31,6 +31,8 @@ SIGNATURES = {
     "gss_stft_packed_i16": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P]),
     "gss_istft_packed": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, c_int64, _P]),
     "gss_mask_istft": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, _P, c_int64, _P]),
+    "gss_stft_packed_dual": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_float, _P, _P, _P]),
+    "gss_mask_istft_feature": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, c_int, _P, c_int64, _P]),
     "gss_apply_mask": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P]),
     "gss_ola_norm_scale": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P]),
     "gss_scale_packed": (c_int, [_P, _P, c_int64, c_int, c_float, c_float, _P]),

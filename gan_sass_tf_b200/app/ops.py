@@ -302,6 +302,56 @@ def _mask_istft_fwd(wave, mask, N, H, out=None):
     return out
 
 
+def stft_dual(wave, fft_size=None, hop=None, out_lin=None, out_log=None):
+    """One transform, both outputs: ``(feature, to_log_signal(feature))`` = the reference's
+    ``s_mixed_signals`` and ``s_mixed_signals_log`` (main.py:328-338) from ``wave [..., n]``.
+    The linear features feed ``mask_istft_feature``; the log features feed the separator."""
+    w = _f32c(wave, "stft_dual")
+    N, H = _nh(fft_size, hop)
+    lead, n = w.shape[:-1], w.shape[-1]
+    T, _ = _n.frame_count(n, N, H)
+    B = 1
+    for d in lead:
+        B *= d
+    shape = lead + (T, N)
+    lin = torch.empty(shape, dtype=torch.float32, device=w.device) if out_lin is None else out_lin
+    lg = torch.empty(shape, dtype=torch.float32, device=w.device) if out_log is None else out_log
+    for o in (lin, lg):
+        assert o.is_cuda and o.dtype == torch.float32 and tuple(o.shape) == tuple(shape) and o.is_contiguous()
+    with torch.cuda.device(w.device):
+        _n.check(_n.lib().gss_stft_packed_dual(w.data_ptr(), B, n, n, N, H, hparams.EPS, lin.data_ptr(), lg.data_ptr(), _stream()))
+    return lin, lg
+
+
+def mask_istft_feature(mix_feature, mask, hop=None, out=None, reverse=False):
+    """Fused ``apply_mask`` + ``istft`` from the mixture's LINEAR packed features ``[B,T,N]`` (what the
+    reference's graph holds as ``s_mixed_signals``, main.py:328-337) and ``mask [B,S,T,N/2]`` ->
+    ``[B*S, (T-1)*H]``, row ``b*S+s``.  Same results as ``istft(apply_mask(f, m))`` without materialising the
+    ``[B*S,T,N]`` product, and as ``mask_istft(wave, m)`` when ``f = stft(wave)``.  ``reverse=True`` walks the rows
+    last-to-first (a cache hint when ``mix_feature`` was written just before; results are identical).
+    Differentiable in both arguments."""
+    _dev(mix_feature, "mask_istft_feature"); _dev(mask, "mask_istft_feature")
+    assert mix_feature.dim() == 3 and mask.dim() == 4, "mask_istft_feature: feature [B,T,N], mask [B,S,T,N/2]"
+    N, H = _nh(mix_feature.shape[-1], hop)
+    if torch.is_grad_enabled() and (mix_feature.requires_grad or mask.requires_grad):
+        assert out is None, "mask_istft_feature: out= is not supported when gradients are required"
+        return _Istft.apply(apply_mask(mix_feature, mask), H, False)
+    f = _f32c(mix_feature, "mask_istft_feature")
+    m = _f32c(mask, "mask_istft_feature")
+    B, T, _ = f.shape
+    S = m.shape[1]
+    assert m.shape == (B, S, T, N // 2), f"mask_istft_feature: mask shape {tuple(m.shape)} != {(B, S, T, N // 2)}"
+    L = (T - 1) * H
+    if out is None:
+        out = torch.empty((B * S, L), dtype=torch.float32, device=f.device)
+    else:
+        assert out.is_cuda and out.dtype == torch.float32 and out.shape == (B * S, L) and out.is_contiguous()
+    with torch.cuda.device(f.device):
+        _n.check(_n.lib().gss_mask_istft_feature(f.data_ptr(), m.data_ptr(), B, S, T, N, H,
+                                                 _n.FLAG_REVERSE if reverse else 0, out.data_ptr(), L, _stream()))
+    return out
+
+
 # ---------------------------------------------------------------------------
 # element-wise compression (reference names)
 # ---------------------------------------------------------------------------

@@ -45,6 +45,10 @@ int stream512_stft_f32(int hs, bool lg, gss::StftArgs<float> a, cudaStream_t st)
 int stream512_stft_i16(int hs, bool lg, gss::StftArgs<int16_t> a, cudaStream_t st);
 int stream512_istft(int hs, bool ex, gss::IstftArgs a, cudaStream_t st);
 int stream512_synth(int hs, gss::SynthArgs a, cudaStream_t st);
+int stream512_stft_dual(int hs, gss::StftArgs<float> a, cudaStream_t st);
+int stream512_synth_feat(int hs, gss::SynthArgs a, cudaStream_t st);
+int stream256_stft_dual(int hs, gss::StftArgs<float> a, cudaStream_t st);
+int stream256_synth_feat(int hs, gss::SynthArgs a, cudaStream_t st);
 int stream256_stft_f32(int hs, bool lg, gss::StftArgs<float> a, cudaStream_t st);
 int stream256_stft_i16(int hs, bool lg, gss::StftArgs<int16_t> a, cudaStream_t st);
 int stream256_istft(int hs, bool ex, gss::IstftArgs a, cudaStream_t st);
@@ -57,6 +61,8 @@ int team_hi_stft_f32(int N, int ths, gss::team::StftArgs<float> t, cudaStream_t 
 int team_hi_stft_i16(int N, int ths, gss::team::StftArgs<int16_t> t, cudaStream_t st);
 int team_hi_istft(int N, int ths, gss::team::IstftArgs t, cudaStream_t st);
 int team_hi_synth(int N, int ths, gss::team::SynthArgs t, cudaStream_t st);
+int team_lo_synth_feat(int N, int ths, gss::team::SynthFeatArgs t, cudaStream_t st);
+int team_hi_synth_feat(int N, int ths, gss::team::SynthFeatArgs t, cudaStream_t st);
 
 }  // namespace gss_shared
 
@@ -267,6 +273,24 @@ int team_synth(gss::team::SynthArgs a, cudaStream_t st) {
     if (a.S == 1) return team_synth_st<N, HS, 1>(a, st);
     return team_synth_st<N, HS, 3>(a, st);
 }
+template <int N, int HS, int ST>
+int team_synth_feat_st(gss::team::SynthFeatArgs a, cudaStream_t st) {
+    auto k = gss::team::mask_istft_feat_kernel<N, HS, ST>;
+    const size_t smem = gss::team::synth_feat_bytes<N>();
+    if (int rc = prep(k, smem)) return rc;
+    a.ngroups = (a.S + ST - 1) / ST;
+    gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::team::TGeo<N, HS>::HALO, cta_slots(k, team_threads<N>(), smem));
+    a.ppc = pl.ppc; a.nchunk = pl.nchunk;
+    k<<<(unsigned)(a.B * a.ngroups * a.nchunk), team_threads<N>(), smem, st>>>(a);
+    return after_launch("team::mask_istft_feat_kernel");
+}
+template <int N, int HS>
+int team_synth_feat(gss::team::SynthFeatArgs a, cudaStream_t st) {
+    if (a.S % 3 == 0) return team_synth_feat_st<N, HS, 3>(a, st);
+    if (a.S % 2 == 0) return team_synth_feat_st<N, HS, 2>(a, st);
+    if (a.S == 1) return team_synth_feat_st<N, HS, 1>(a, st);
+    return team_synth_feat_st<N, HS, 3>(a, st);
+}
 // F<N, HS>::run(args...) for the (N, hs) pairs the team kernels cover
 #define GSS_TEAM_DISPATCH_LO(N, hs, CALL)                                                                           \
     do {                                                                                                            \
@@ -281,9 +305,9 @@ int team_synth(gss::team::SynthArgs a, cudaStream_t st) {
     } while (0)
 
 // ---- STFT ---------------------------------------------------------------
-template <int N, int HS, bool LOG, typename TIn, int WARPS = 4>
+template <int N, int HS, bool LOG, typename TIn, int WARPS = 4, bool DUAL = false>
 int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
-    auto k = gss::stft_kernel<N, HS, LOG, TIn, WARPS>;
+    auto k = gss::stft_kernel<N, HS, LOG, TIn, WARPS, DUAL>;
     constexpr int TEAMS = WARPS * 32 / gss::Geo<N>::TPF;       // transforms in flight per CTA
     const size_t smem = team_smem<N>(TEAMS);
     if (int rc = prep(k, smem)) return rc;
@@ -362,11 +386,11 @@ int launch_istft(gss::IstftArgs a, cudaStream_t st) {
 }
 
 // ---- fused synthesis ------------------------------------------------------
-template <int N, int HS, int ST, int WARPS = 4>
+template <int N, int HS, int ST, int WARPS = 4, bool FEAT = false>
 int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
-    auto k = gss::mask_istft_kernel<N, HS, ST, WARPS>;
+    auto k = gss::mask_istft_kernel<N, HS, ST, WARPS, FEAT>;
     constexpr int TEAMS = WARPS * 32 / gss::Geo<N>::TPF;
-    size_t smem = gss::SynthSmem<N, ST>::bytes(TEAMS);
+    size_t smem = gss::SynthSmem<N, ST, FEAT>::bytes(TEAMS);
 #ifdef GSS_TUNE
     smem += (size_t)tune("GSS_EXTRA_SMEM", 0);      // occupancy limiter for single-warp-per-SMSP experiments
 #endif
@@ -474,6 +498,16 @@ int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
     return launch_synth<N, HS, 3>(a, st);
 }
 
+// feature-fed synthesis (gss_mask_istft_feature): same source grouping
+template <int N, int HS>
+int synth_feat_by_s(gss::SynthArgs a, cudaStream_t st) {
+    if (a.S % 3 == 0) return launch_synth_w<N, HS, 3, 4, true>(a, st);
+    if (a.S % 4 == 0 && HS == 2) return launch_synth_w<N, HS, 4, 4, true>(a, st);
+    if (a.S % 2 == 0) return launch_synth_w<N, HS, 2, 4, true>(a, st);
+    if (a.S == 1) return launch_synth_w<N, HS, 1, 4, true>(a, st);
+    return launch_synth_w<N, HS, 3, 4, true>(a, st);
+}
+
 // ---- bridges between the parts (declared in gss_shared at the top of the file) ----------------------
 }  // namespace GSS_NS
 namespace gss_shared {
@@ -498,6 +532,16 @@ using namespace GSS_NS;
         if (hs == 1) return synth_by_s<NN, 1>(a, st);                                                                \
         if (hs == 2) return synth_by_s<NN, 2>(a, st);                                                                \
         return synth_by_s<NN, 4>(a, st);                                                                             \
+    }                                                                                                                \
+    int stream##NN##_stft_dual(int hs, gss::StftArgs<float> a, cudaStream_t st) {                                    \
+        if (hs == 1) return launch_stft_w<NN, 1, true, float, 4, true>(a, st);                                       \
+        if (hs == 2) return launch_stft_w<NN, 2, true, float, 4, true>(a, st);                                       \
+        return launch_stft_w<NN, 4, true, float, 4, true>(a, st);                                                    \
+    }                                                                                                                \
+    int stream##NN##_synth_feat(int hs, gss::SynthArgs a, cudaStream_t st) {                                         \
+        if (hs == 1) return synth_feat_by_s<NN, 1>(a, st);                                                           \
+        if (hs == 2) return synth_feat_by_s<NN, 2>(a, st);                                                           \
+        return synth_feat_by_s<NN, 4>(a, st);                                                                        \
     }
 #if GSS_HAS(1)
 #ifdef GSS_QUICK   // tuning builds only (tools/variant.sh): the C2 kernels alone, seconds instead of minutes to compile
@@ -514,6 +558,14 @@ int stream512_synth(int hs, gss::SynthArgs a, cudaStream_t st) {
     if (hs != 2 || a.S != 3) return fail(GSS_EUNSUPPORTED, "GSS_QUICK build: hop N/4, S = 3 only");
     if (synth_variant() == 2) return launch_synth_tm<512, 2, 3>(a, st);
     return launch_synth<512, 2, 3>(a, st);
+}
+int stream512_stft_dual(int hs, gss::StftArgs<float> a, cudaStream_t st) {
+    if (hs != 2) return fail(GSS_EUNSUPPORTED, "GSS_QUICK build: hop N/4 only");
+    return launch_stft_w<512, 2, true, float, 4, true>(a, st);
+}
+int stream512_synth_feat(int hs, gss::SynthArgs a, cudaStream_t st) {
+    if (hs != 2 || a.S != 3) return fail(GSS_EUNSUPPORTED, "GSS_QUICK build: hop N/4, S = 3 only");
+    return launch_synth_w<512, 2, 3, 4, true>(a, st);
 }
 #else
 GSS_STREAM_PART(512)
@@ -532,11 +584,14 @@ GSS_STREAM_PART(256)
     int NAME##_istft(int N, int ths, gss::team::IstftArgs t, cudaStream_t st) {                                      \
         DISPATCH(N, ths, GSS_CALL_ISTFT); return fail(GSS_EUNSUPPORTED, "team istft: no kernel for N=%d", N); }      \
     int NAME##_synth(int N, int ths, gss::team::SynthArgs t, cudaStream_t st) {                                      \
-        DISPATCH(N, ths, GSS_CALL_SYNTH); return fail(GSS_EUNSUPPORTED, "team mask_istft: no kernel for N=%d", N); }
+        DISPATCH(N, ths, GSS_CALL_SYNTH); return fail(GSS_EUNSUPPORTED, "team mask_istft: no kernel for N=%d", N); }  \
+    int NAME##_synth_feat(int N, int ths, gss::team::SynthFeatArgs t, cudaStream_t st) {                             \
+        DISPATCH(N, ths, GSS_CALL_SYNTH_FEAT); return fail(GSS_EUNSUPPORTED, "team mask_istft_feature: no kernel for N=%d", N); }
 #define GSS_CALL_STFT_F32(NN, HH) return team_stft<NN, HH, float>(t, st);
 #define GSS_CALL_STFT_I16(NN, HH) return team_stft<NN, HH, int16_t>(t, st);
 #define GSS_CALL_ISTFT(NN, HH) return team_istft<NN, HH>(t, st);
 #define GSS_CALL_SYNTH(NN, HH) return team_synth<NN, HH>(t, st);
+#define GSS_CALL_SYNTH_FEAT(NN, HH) return team_synth_feat<NN, HH>(t, st);
 #if GSS_HAS(3)
 GSS_TEAM_PART(team_lo, GSS_TEAM_DISPATCH_LO)
 #endif
@@ -702,6 +757,63 @@ int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64
         return launch_ola_generic<true>(g, st);
     }
     return N == 512 ? stream512_synth(hs, a, st) : stream256_synth(hs, a, st);
+}
+
+int gss_stft_packed_dual(const float* wave, int64_t B, int64_t n, int64_t ld, int N, int H, float eps,
+                         float* feat_lin, float* feat_log, void* stream) {
+    int hs = 0;
+    if (int rc = check_nh(N, H, &hs)) return rc;
+    if (!wave || !feat_lin || !feat_log) return fail(GSS_EINVAL, "stft_dual: null pointer");
+    if (B < 0 || n < 1 || ld < n) return fail(GSS_EINVAL, "stft_dual: bad shape B=%lld n=%lld ld=%lld", (long long)B, (long long)n, (long long)ld);
+    if (n < N) return fail(GSS_EUNSUPPORTED, "stft_dual: n=%lld < FFT_SIZE=%d (SciPy would silently shrink nperseg)", (long long)n, N);
+    if (B == 0) return GSS_OK;
+    if (!fast_n(N)) {
+        int64_t T = 0;
+        if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
+        if (const int ths = team_hs(N, H)) {
+            gss::team::StftArgs<float> t{};
+            t.wave = wave; t.feat = feat_log; t.feat_lin = feat_lin; t.B = B; t.n = n; t.ld = ld; t.T = T;
+            t.npairs = (int)((T + 1) / 2); t.log = 1; t.eps = eps;
+            return N <= 1024 ? team_lo_stft_f32(N, ths, t, (cudaStream_t)stream) : team_hi_stft_f32(N, ths, t, (cudaStream_t)stream);
+        }
+        // sizes without a streaming kernel: the plain transform, then to_log over its output (two launches)
+        if (int rc = gss_stft_packed(wave, B, n, ld, N, H, 0, eps, feat_lin, stream)) return rc;
+        return gss_to_log(feat_lin, feat_log, B * T, N, eps, stream);
+    }
+    gss::StftArgs<float> a{};
+    a.wave = wave; a.feat = feat_log; a.feat_lin = feat_lin; a.B = B; a.n = n; a.ld = ld; a.eps = eps;
+    a.al_in = ((uintptr_t)wave % 8 == 0) && (ld % 2 == 0 || B == 1);
+    if (int rc = frame_count(n, N, H, &a.T, nullptr)) return rc;
+    a.npairs = (int)((a.T + 1) / 2);
+    return N == 512 ? stream512_stft_dual(hs, a, (cudaStream_t)stream) : stream256_stft_dual(hs, a, (cudaStream_t)stream);
+}
+
+int gss_mask_istft_feature(const float* feat, const float* mask, int64_t B, int S, int64_t T, int N, int H, int flags,
+                           float* out, int64_t ld_out, void* stream) {
+    int hs = 0;
+    if (int rc = check_nh(N, H, &hs)) return rc;
+    if (!feat || !mask || !out) return fail(GSS_EINVAL, "mask_istft_feature: null pointer");
+    if (B < 0 || S < 1 || T < 2) return fail(GSS_EINVAL, "mask_istft_feature: bad shape B=%lld S=%d T=%lld", (long long)B, S, (long long)T);
+    if (flags & ~GSS_FLAG_REVERSE) return fail(GSS_EINVAL, "mask_istft_feature: unknown flags 0x%x", flags);
+    if (((uintptr_t)mask | (uintptr_t)feat) % 16) return fail(GSS_EINVAL, "mask_istft_feature: features and masks must be 16-byte aligned (TMA bulk copies)");
+    if (ld_out < (T - 1) * H) return fail(GSS_EINVAL, "mask_istft_feature: ld_out=%lld < (T-1)*H=%lld", (long long)ld_out, (long long)((T - 1) * H));
+    if (B == 0) return GSS_OK;
+    if (!fast_n(N)) {
+        if (const int ths = team_hs(N, H)) {
+            gss::team::SynthFeatArgs t{};
+            t.feat = feat; t.mask = mask; t.out = out; t.B = B; t.T = T; t.ld_out = ld_out; t.S = S;
+            t.npairs = (int)((T + 1) / 2); t.rev = (flags & GSS_FLAG_REVERSE) ? 1 : 0;
+            return N <= 1024 ? team_lo_synth_feat(N, ths, t, (cudaStream_t)stream) : team_hi_synth_feat(N, ths, t, (cudaStream_t)stream);
+        }
+        return fail(GSS_EUNSUPPORTED, "mask_istft_feature: FFT_SIZE %d has no feature-fed synthesis kernel (256 ... 4096 do); use gss_apply_mask + gss_istft_packed", N);
+    }
+    gss::SynthArgs a{};
+    a.feat = feat; a.mask = mask; a.out = out; a.B = B; a.T = T; a.ld_out = ld_out; a.S = S;
+    a.rev = (flags & GSS_FLAG_REVERSE) ? 1 : 0;
+    a.al_in = 1;
+    a.al_out = ((uintptr_t)out % 8 == 0) && (ld_out % 2 == 0 || B * S == 1);
+    a.npairs = (int)((T + 1) / 2);
+    return N == 512 ? stream512_synth_feat(hs, a, (cudaStream_t)stream) : stream256_synth_feat(hs, a, (cudaStream_t)stream);
 }
 
 int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_t T, int N, float* out, void* stream) {

@@ -381,13 +381,16 @@ __device__ __forceinline__ v2 log_gain2_tiny(v2 a2, float eps) {
 template <typename TIn>
 struct StftArgs {
     const TIn* wave; float* feat;
+    float* feat_lin;                // DUAL kernels (gss_stft_packed_dual): the linear packed spectrum beside the log features
     int64_t B, n, ld, T;
     int npairs, ppc, nchunk;
     int al_in;                      // every row start is aligned for 2-sample vector loads
     float eps;
 };
 
-template <int N, int HS, bool LOG, typename TIn, int WARPS>
+// DUAL (with LOG): the linear spectrum goes to p.feat_lin and its to_log to p.feat - what the separator reads and what
+// the feature-fed synthesis (gss_mask_istft_feature) multiplies the masks into, from one transform.
+template <int N, int HS, bool LOG, typename TIn, int WARPS, bool DUAL = false>
 __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? GSS_STFT_MAXREG : ((65536 / (WARPS * 32)) / 8) * 8) stft_kernel(const StftArgs<TIn> p) {
     typedef SGeo<N, HS> SG; typedef Geo<N> G;
     extern __shared__ float4 smem4[];
@@ -423,6 +426,7 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? GSS_STFT_
     load_slots<SG::L, SG::RS>(row, p.n, base, j, al, ring);
     const TIn* wptr = row + (base + SG::RS - 4) * SG::L + 2 * j;      // slot base + RS: first slot the next pair adds
     float* fptr = p.feat + (b * p.T + 2 * (int64_t)q0) * N;           // feature row of frame 2q
+    float* lptr = DUAL ? p.feat_lin + (b * p.T + 2 * (int64_t)q0) * N : nullptr;
 
     auto step = [&](int q, auto tag) {
         constexpr bool FAST = decltype(tag)::value;
@@ -439,6 +443,23 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? GSS_STFT_
         PairSpec s;
         split_pair<N>(a, t0, s);
 
+        if (DUAL) {
+            float* ra = lptr + ctx.cA;
+            float* rb = lptr + ctx.cB;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ra[SG::L * i] = s.ar[i].x; ra[N / 2 + SG::L * i] = s.ai[i].x;
+                rb[SG::L * i] = s.ar[i].y; rb[N / 2 + SG::L * i] = s.ai[i].y;
+            }
+            if (FAST || 2 * (int64_t)q + 1 < p.T) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ra[N + SG::L * i] = s.br[i].x; ra[N + N / 2 + SG::L * i] = s.bi[i].x;
+                    rb[N + SG::L * i] = s.br[i].y; rb[N + N / 2 + SG::L * i] = s.bi[i].y;
+                }
+            }
+            lptr += 2 * N;
+        }
         if (LOG) {
             v2 a2a[4], a2b[4];
             float mx = 0.f;
@@ -641,6 +662,8 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 && !EXP ? 1
 #endif
 struct SynthArgs {
     const float* wave; const float* mask; float* out;
+    const float* feat;              // FEAT kernels: linear packed mixture spectrum [B, T, N] instead of `wave`
+    int rev;                        // FEAT kernels: walk the work items from the last row to the first
     long long* timing;              // [items][8] cycle accumulators (GSS_TIMING builds only)
     int64_t B, n, ld, T, ld_out;
     int S, ngroups;                 // ngroups = ceil(S / ST)
@@ -648,13 +671,15 @@ struct SynthArgs {
     int al_in, al_out;
 };
 
-template <int N, int ST>
+template <int N, int ST, bool FEAT = false>
 struct SynthSmem {
     static constexpr int NH = N / 2;
     static constexpr int STAGE_FLOATS = ST * 2 * NH;              // per team, per stage
-    static constexpr int TEAM_FLOATS = Geo<N>::TEAM_FLOATS + 2 * STAGE_FLOATS;
-    static constexpr size_t bytes(int warps) {
-        return sizeof(float) * ((size_t)warps * TEAM_FLOATS) + sizeof(uint64_t) * 2 * warps;
+    static constexpr int FSTAGE_FLOATS = FEAT ? 2 * N : 0;        // FEAT: the pair's two packed feature rows (single stage)
+    static constexpr int TEAM_FLOATS = Geo<N>::TEAM_FLOATS + 2 * STAGE_FLOATS + FSTAGE_FLOATS;
+    static constexpr int NBAR = 3;                                // two mask stages + the feature stage
+    static constexpr size_t bytes(int teams) {
+        return sizeof(float) * ((size_t)teams * TEAM_FLOATS) + sizeof(uint64_t) * NBAR * teams;
     }
 };
 
@@ -686,9 +711,12 @@ __device__ __forceinline__ void mask_pack_pair(const PairSpec& x, const v2 (&ga)
     }
 }
 
-template <int N, int HS, int ST, int WARPS>
+// FEAT = true (gss_mask_istft_feature): the mixture's LINEAR packed spectrum [B, T, N] is read back (one 1-D TMA bulk
+// copy of the pair's two feature rows per iteration) instead of being recomputed from the waveform: one of the
+// 1 + ST transforms per pair goes away (the kernel is bound by issue slots, not by bytes), for 4TN - 4n more bytes.
+template <int N, int HS, int ST, int WARPS, bool FEAT = false>
 __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((65536 / (WARPS * 32)) / 8) * 8) mask_istft_kernel(const SynthArgs p) {
-    typedef SGeo<N, HS> SG; typedef Geo<N> G; typedef SynthSmem<N, ST> SM;
+    typedef SGeo<N, HS> SG; typedef Geo<N> G; typedef SynthSmem<N, ST, FEAT> SM;
     constexpr int NH = N / 2;
     extern __shared__ float4 smem4[];
     float* smf = reinterpret_cast<float*>(smem4);
@@ -696,12 +724,14 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
     const int warp = threadIdx.x / G::TPF, j = threadIdx.x % G::TPF;       // team index inside the CTA, lane inside the team
     float* team = smf + warp * SM::TEAM_FLOATS;
     float* stage = team + G::TEAM_FLOATS;                                  // 2 x STAGE_FLOATS, 16-byte aligned
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smf + TEAMS * SM::TEAM_FLOATS) + 2 * warp;
-    if (j == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    float* fstage = stage + 2 * SM::STAGE_FLOATS;                          // FEAT: 2 x N floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smf + TEAMS * SM::TEAM_FLOATS) + SM::NBAR * warp;
+    if (j == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
     __syncthreads();
-    const int64_t item = (int64_t)blockIdx.x * TEAMS + warp;
     const int64_t per_b = (int64_t)p.ngroups * p.nchunk;
+    int64_t item = (int64_t)blockIdx.x * TEAMS + warp;
     if (item >= p.B * per_b) return;
+    if (FEAT && p.rev) item = p.B * per_b - 1 - item;
     const int64_t b = item / per_b;
     const int rem = (int)(item - b * per_b);
     const int grp = rem / p.nchunk, c = rem - grp * p.nchunk;
@@ -714,10 +744,10 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
     TeamCtx<N> ctx;
     team_init_tab<N>(ctx, j, team);
     v2 win[8];                                     // hann / N: analysis scale; synthesis rescaled at the store
-    window_tab<N>(j, 1.0f / (float)N, win);
+    window_tab<N>(j, FEAT ? 1.0f : 1.0f / (float)N, win);
 
     OlaOut<SG> o;
-    o.init(p.T, j, p.al_out != 0, (float)N);
+    o.init(p.T, j, p.al_out != 0, FEAT ? 1.0f : (float)N);
     float* orow0 = p.out + (b * p.S + s0) * p.ld_out;
     const float* mrow0 = p.mask + ((b * p.S + s0) * p.T) * NH;       // source s: + s*T*NH; frame t: + t*NH
     const int64_t msrc = p.T * NH;                                   // mask stride between sources
@@ -743,14 +773,29 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
         }
     };
 
-    const float* row = p.wave + b * p.ld;
-    const bool al = p.al_in != 0;
+    // FEAT: one lane stages the two packed feature rows of pair q (single stage: refilled as soon as every lane has
+    // consumed the previous pair's values, see `source`)
+    const float* frow = FEAT ? p.feat + b * p.T * N : nullptr;
+    const uint32_t fstage_s = smem_u32(fstage);
+    auto prefetch_feat = [&](int q) {
+        if (G::TPF >= 32 ? elect_one() : j == 0) {
+            const int64_t ta = 2 * (int64_t)q;
+            const uint32_t bytes = (ta + 1 < p.T ? 2 : 1) * N * (uint32_t)sizeof(float);
+            const uint32_t bar = bars_s + 16u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(fstage_s), "l"(frow + ta * N), "r"(bytes), "r"(bar) : "memory");
+        }
+    };
+
+    const float* row = FEAT ? nullptr : p.wave + b * p.ld;
+    const bool al = FEAT || p.al_in != 0;
 
     // fast stretch [qa, qb): own pairs whose input slots (incl. the next pair's loads) lie inside the
     // signal, whose ADV output slots are interior (covered by R frames), with both frames present
     int qa, qb;
     {
-        int64_t qhi = fast_hi_input<SG>(p.n);
+        int64_t qhi = FEAT ? (int64_t)1 << 40 : fast_hi_input<SG>(p.n);
         const int64_t hi_out = (p.T - 1) * HS + (HS < 4 ? HS : 4) - SG::ADV;     // base + ADV <= (T-1)HS + min(HS,4)
         const int64_t qo = hi_out < 0 ? -1 : hi_out / (2 * HS);
         if (qo < qhi) qhi = qo;
@@ -769,10 +814,11 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
         for (int i = 0; i < SG::KEEP; ++i) acc[s][i] = make_float2(0.f, 0.f);
 
     int64_t base = (int64_t)2 * qs * HS;
-    v2 ring[SG::RS];
+    v2 ring[FEAT ? 1 : SG::RS];
     prefetch(qs);
-    load_slots<SG::L, SG::RS>(row, p.n, base, j, al, ring);
-    const float* wptr = row + (base + SG::RS - 4) * SG::L + 2 * j;      // first slot the next pair adds
+    if constexpr (FEAT) prefetch_feat(qs);
+    else load_slots<SG::L, SG::RS>(row, p.n, base, j, al, ring);
+    const float* wptr = FEAT ? nullptr : row + (base + SG::RS - 4) * SG::L + 2 * j;      // first slot the next pair adds
     float* optr = orow0 + (base - 4) * SG::L + 2 * j;                   // output slot `base` of source s0
     const float* mA = stage + ctx.cA;
     const float* mB = stage + ctx.cB;
@@ -784,7 +830,21 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
         constexpr bool FAST = decltype(tag)::value;
         GSS_T(7);
         PairSpec x;
-        {
+        const bool hb = FAST || 2 * (int64_t)q + 1 < p.T;
+        if constexpr (FEAT) {
+            // the other mask stage was last read in iteration q-1; every lane has passed a __syncwarp since
+            if (q + 1 < q1) prefetch(q + 1);
+            mbar_wait(&bars[2], (uint32_t)(q - qs) & 1u);
+            const float* fa = fstage + ctx.cA;
+            const float* fb = fstage + ctx.cB;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                x.ar[i] = make_float2(fa[SG::L * i], fb[SG::L * i]);
+                x.ai[i] = make_float2(fa[NH + SG::L * i], fb[NH + SG::L * i]);
+                x.br[i] = hb ? make_float2(fa[N + SG::L * i], fb[N + SG::L * i]) : make_float2(0.f, 0.f);
+                x.bi[i] = hb ? make_float2(fa[N + NH + SG::L * i], fb[N + NH + SG::L * i]) : make_float2(0.f, 0.f);
+            }
+        } else {
             cv2 a[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a[i].re = vmul(ring[i], win[i]); a[i].im = vmul(ring[HS + i], win[i]); }
@@ -800,7 +860,6 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
             split_pair<N>(a, t0, x);
         }
         GSS_T(0);
-        const bool hb = FAST || 2 * (int64_t)q + 1 < p.T;
         const int stg = (q - qs) & 1;
         mbar_wait(&bars[stg], ((q - qs) >> 1) & 1);
         GSS_T(1);
@@ -820,6 +879,11 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
             cv2 a[8];
             mask_pack_pair<N>(x, ga, gb, t0, a);
             GSS_T(2);
+            if constexpr (FEAT) {
+                // every lane's values of this pair's feature rows have been consumed by the multiplies above
+                // (the loads have landed); after the team barrier the single feature stage can be refilled
+                if (s == 0 && q + 1 < q1) { team_sync(ctx); prefetch_feat(q + 1); }
+            }
             fft_inverse<N>(ctx, a);
             GSS_T(3);
             v2 cur[SG::RS];

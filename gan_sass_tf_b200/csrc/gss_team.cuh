@@ -344,6 +344,7 @@ __device__ __forceinline__ void ola_accumulate(const float2 (&v)[G::R0], const f
 template <typename TIn>
 struct StftArgs {
     const TIn* wave; float* feat;
+    float* feat_lin;                // not null (gss_stft_packed_dual): the linear spectrum goes here, its to_log to `feat`
     int64_t B, n, ld, T;
     int npairs, ppc, nchunk;
     int log; float eps;
@@ -386,6 +387,11 @@ __global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB) stft_kernel(c
                 const float2 zh = A[pad<R0>(N / 2)];
                 split_bin(zh, zh, An, Bn);
                 Sa.y = An.x; Sb.y = Bn.x;
+            }
+            if (p.feat_lin) {
+                float* la = p.feat_lin + (b * p.T + ta) * N;
+                la[k] = Sa.x; la[N / 2 + k] = Sa.y;
+                if (hb) { la[N + k] = Sb.x; la[N + N / 2 + k] = Sb.y; }
             }
             if (p.log) {
                 float g = log_gain_warp(Sa.x, Sa.y, p.eps); Sa.x *= g; Sa.y *= g;
@@ -576,6 +582,153 @@ __global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_SYNTH) mask_is
                     float2 Sa, Sb;
                     split_bin(X[pad<R0>(NH)], X[pad<R0>(NH)], Sa, Sb);
                     pack_bin<R0>(make_float2(Sa.x * ga[0], Sa.y * ga[0]), make_float2(Sb.x * gb[0], Sb.y * gb[0]), Y, NH, N);
+                }
+                __syncthreads();
+                float2 v[R0];
+                inverse_to_regs<G>(Y, W, v, tw, t);
+                float cur[G::RS];
+#pragma unroll
+                for (int i = 0; i < G::RS; ++i) cur[i] = i < G::KEEP ? acc[s][i] : 0.f;
+                ola_accumulate<G>(v, win, cur);
+                if (own) {
+                    float* orow = orow0 + s * p.ld_out;
+                    if (fast) {
+#pragma unroll
+                        for (int i = 0; i < G::ADV; ++i) o.write_fast(orow, base + i, i % HS, cur[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < G::ADV; ++i) o.write(orow, base + i, i % HS, cur[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < G::KEEP; ++i) acc[s][i] = cur[i + G::ADV];
+#pragma unroll
+                for (int i = 0; i < KI; ++i) { ga[i] = ga_n[i]; gb[i] = gb_n[i]; }
+                __syncthreads();                    // Y (read by the last pass) is rewritten by the next source's pack
+            }
+        }
+        base += G::ADV;
+    }
+    if (c == p.nchunk - 1) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s)
+            if (s < ns) {
+#pragma unroll
+                for (int i = 0; i < G::KEEP; ++i) o.write(orow0 + s * p.ld_out, base + i, i % HS, acc[s][i]);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// feature-fed synthesis (gss_mask_istft_feature): the mixture's linear packed spectrum [B, T, N] is read back
+// instead of being recomputed from the waveform - ST instead of 1 + ST transforms per frame pair.  The two feature
+// rows of a pair (2N contiguous floats) arrive by one 1-D TMA bulk copy into a double-buffered stage, one pair
+// ahead; every thread keeps its own bins (k = t + i*TPT) of the pair in registers for all ST sources.
+// ---------------------------------------------------------------------------
+struct SynthFeatArgs {
+    const float* feat; const float* mask; float* out;
+    int64_t B, T, ld_out;
+    int S, ngroups;
+    int npairs, ppc, nchunk;
+    int rev;
+};
+template <int N> constexpr size_t synth_feat_bytes() {
+    return sizeof(float2) * 2 * (size_t)(N + N / Plan<N>::R0) + sizeof(float) * 4 * (size_t)N + 2 * sizeof(uint64_t);
+}
+
+template <int N, int HS, int ST>
+__global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_SYNTH) mask_istft_feat_kernel(const SynthFeatArgs p) {
+    typedef TGeo<N, HS> G;
+    constexpr int NH = N / 2, R0 = G::R0;
+    extern __shared__ float4 smem4[];
+    float2* Y = reinterpret_cast<float2*>(smem4);
+    float2* W = Y + G::PADN;
+    float* F = reinterpret_cast<float*>(W + G::PADN);            // 2 stages x 2N floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(F + 4 * N);
+    const int t = threadIdx.x;
+    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    const int64_t per_b = (int64_t)p.ngroups * p.nchunk;
+    int64_t item = blockIdx.x;
+    if (p.rev) item = p.B * per_b - 1 - item;
+    const int64_t b = item / per_b;
+    const int rem = (int)(item - b * per_b);
+    const int grp = rem / p.nchunk, c = rem - grp * p.nchunk;
+    const int s0 = grp * ST;
+    const int ns = min(ST, p.S - s0);
+    const int q0 = c * p.ppc, q1 = min(q0 + p.ppc, p.npairs);
+    const int qs = max(q0 - G::HALO, 0);
+
+    TeamTw<G> tw; init_tw<G>(tw, t);
+    float win[G::FS];
+    make_window<G>(t, 1.0f, win);
+    Ola<G> o;
+    o.init(p.T, t, 1.0f);
+    float* orow0 = p.out + (b * p.S + s0) * p.ld_out;
+    const float* mrow0 = p.mask + ((b * p.S + s0) * p.T) * NH;
+    const int64_t msrc = p.T * NH;
+    const float* frow = p.feat + b * p.T * N;
+
+    auto stage_features = [&](int q_) {
+        if (t == 0) {
+            const int st = (q_ - qs) & 1;
+            const int64_t ta_ = 2 * (int64_t)q_;
+            const uint32_t bytes = (ta_ + 1 < p.T ? 2 : 1) * N * (uint32_t)sizeof(float);
+            mbar_expect_tx(&bars[st], bytes);
+            tma_load_1d(F + st * 2 * N, frow + ta_ * N, bytes, &bars[st]);
+        }
+    };
+
+    float acc[ST][G::KEEP];
+#pragma unroll
+    for (int s = 0; s < ST; ++s)
+#pragma unroll
+        for (int i = 0; i < G::KEEP; ++i) acc[s][i] = 0.f;
+    int64_t base = (int64_t)2 * qs * HS;
+
+    constexpr int KI = NH / G::TPT;
+    auto fetch = [&](int q_, int s, float (&a)[KI], float (&bq)[KI]) {
+        const int64_t ta_ = 2 * (int64_t)q_;
+        const bool hb_ = ta_ + 1 < p.T;
+        const float* ma = mrow0 + s * msrc + ta_ * NH + t;
+#pragma unroll
+        for (int i = 0; i < KI; ++i) { a[i] = ldg_here(ma + i * G::TPT); bq[i] = hb_ ? ldg_here(ma + NH + i * G::TPT) : 0.f; }
+    };
+    float ga[KI], gb[KI], ga_n[KI], gb_n[KI];
+    stage_features(qs);
+    fetch(qs, 0, ga_n, gb_n);
+
+    for (int q = qs; q < q1; ++q) {
+        // the other stage was last read at the top of pair q-1; CTA barriers have passed since
+        if (q + 1 < q1) stage_features(q + 1);
+        const int st = (q - qs) & 1;
+        mbar_wait(&bars[st], (uint32_t)((q - qs) >> 1) & 1u);
+        const bool hb = 2 * (int64_t)q + 1 < p.T;
+        const float* f = F + st * 2 * N + t;
+        float2 Sa[KI], Sb[KI];
+#pragma unroll
+        for (int i = 0; i < KI; ++i) {
+            Sa[i] = make_float2(f[i * G::TPT], f[NH + i * G::TPT]);
+            Sb[i] = hb ? make_float2(f[N + i * G::TPT], f[N + NH + i * G::TPT]) : make_float2(0.f, 0.f);
+        }
+        const bool own = q >= q0;
+        const bool fast = o.interior(base);
+#pragma unroll
+        for (int i = 0; i < KI; ++i) { ga[i] = ga_n[i]; gb[i] = gb_n[i]; }
+#pragma unroll
+        for (int s = 0; s < ST; ++s) {
+            if (s < ns) {
+                if (s + 1 < ns) fetch(q, s + 1, ga_n, gb_n);
+                else if (q + 1 < q1) fetch(q + 1, 0, ga_n, gb_n);
+#pragma unroll
+                for (int i = 0; i < KI; ++i) {
+                    const int k = t + i * G::TPT;
+                    float2 Ya = make_float2(Sa[i].x * ga[i], Sa[i].y * ga[i]), Yb = make_float2(Sb[i].x * gb[i], Sb[i].y * gb[i]);
+                    if (k == 0) {         // slot 0 = (DC, Nyquist): bin 0 -> (f[0], 0), bin N/2 -> (f[N/2], 0), one shared gain
+                        pack_bin<R0>(make_float2(Ya.y, 0.f), make_float2(Yb.y, 0.f), Y, NH, N);
+                        Ya.y = 0.f; Yb.y = 0.f;
+                    }
+                    pack_bin<R0>(Ya, Yb, Y, k, N);
                 }
                 __syncthreads();
                 float2 v[R0];

@@ -38,7 +38,9 @@ typedef enum {
 
 enum {
     GSS_FLAG_LOG = 1,       /* fuse to_log_signal (app/ops.py:228-238) into the STFT epilogue  */
-    GSS_FLAG_EXP = 2        /* fuse to_exp_signal (app/ops.py:241-251) into the iSTFT prologue */
+    GSS_FLAG_EXP = 2,       /* fuse to_exp_signal (app/ops.py:241-251) into the iSTFT prologue */
+    GSS_FLAG_REVERSE = 4    /* gss_mask_istft_feature: walk the rows from the last to the first - a hint for callers
+                               whose features were written moments earlier (the tail is still in L2); same results */
 };
 
 int         gss_version(void);
@@ -93,6 +95,22 @@ int gss_istft_packed(const float* feat, int64_t R, int64_t T, int N, int H,
  *   (the output order of app/modules.py:396-399), (T-1)*H samples per row. */
 int gss_mask_istft(const float* wave, const float* mask, int64_t B, int S, int64_t n, int64_t ld,
                    int N, int H, float* out, int64_t ld_out, void* stream);
+
+/* A1+A2+A3 with both outputs: the linear packed spectrum (what main.py:328-337 calls s_mixed_signals and what a
+ * mask is applied to) and its to_log_signal (what the separator reads, main.py:338) from ONE transform.
+ *   wave [B, ld] f32 -> feat_lin [B, T, N] f32, feat_log [B, T, N] f32. */
+int gss_stft_packed_dual(const float* wave, int64_t B, int64_t n, int64_t ld, int N, int H, float eps,
+                         float* feat_lin, float* feat_log, void* stream);
+
+/* A7+A8 fused, fed by the mixture's LINEAR packed spectrum (the reference's own data flow: its graph holds the
+ * mixture as packed features, main.py:328-337, not as a waveform) instead of recomputing it from the waveform:
+ *   feat [B, T, N] f32, mask [B, S, T, N/2] f32 -> out [B*S, ld_out] f32, row b*S+s, (T-1)*H samples per row.
+ * Same results as gss_apply_mask + gss_istft_packed and as gss_mask_istft on the waveform the features came from;
+ * trades 4TN - 4n more bytes read per mixture for one transform fewer per frame pair.  FFT_SIZE 256 / 512 have the
+ * register-exchange kernel, 1024 / 2048 / 4096 the team kernel; other sizes return GSS_EUNSUPPORTED.
+ * feat and mask 16-byte aligned (TMA bulk copies).  flags: 0 or GSS_FLAG_REVERSE. */
+int gss_mask_istft_feature(const float* feat, const float* mask, int64_t B, int S, int64_t T, int N, int H, int flags,
+                           float* out, int64_t ld_out, void* stream);
 
 /* A7 alone on packed features: mix [B,T,N], mask [B,S,T,N/2] -> out [B*S,T,N] */
 int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_t T, int N,

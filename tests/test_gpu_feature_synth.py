@@ -1,0 +1,117 @@
+"""GPU parity of the feature-fed synthesis (gss_mask_istft_feature) and the dual-output STFT
+(gss_stft_packed_dual): against the CPU oracle, against the waveform-fed kernel, and against the
+unfused composition apply_mask -> istft (reference data flow main.py:328-342).
+"""
+import numpy as np
+import pytest
+
+from oracle import ref_oracle as R
+
+pytestmark = pytest.mark.gpu
+REL_L2 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gan_sass_tf_b200.app import ops as o
+    from gan_sass_tf_b200 import _native
+    _native.lib()
+    return o
+
+
+def dev(T, a):
+    return T.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+CASES = [
+    (512, 128, 4797, 2, 3), (512, 128, 6000, 1, 4), (512, 128, 5000, 2, 1), (512, 128, 5000, 1, 2), (512, 128, 3000, 1, 5),
+    (512, 256, 5000, 2, 3), (512, 64, 3000, 1, 3), (256, 128, 3000, 2, 4), (256, 64, 2500, 3, 3), (256, 32, 1500, 1, 2),
+    (512, 128, 512, 1, 3), (512, 128, 640, 2, 3), (512, 128, 48000, 2, 3),
+    (1024, 256, 9000, 1, 3), (1024, 512, 9000, 2, 2), (1024, 128, 5000, 1, 1), (2048, 512, 9000, 1, 3), (4096, 1024, 20000, 1, 3),
+    (4096, 2048, 20000, 2, 4),
+]
+
+
+@pytest.mark.parametrize("N,H,n,B,S", CASES)
+def test_mask_istft_feature_matches_oracle(T, ops, N, H, n, B, S):
+    rng = np.random.default_rng(N + n + S)
+    x = (rng.standard_normal((B, n)) * 0.1).astype(np.float32)
+    Tn, _ = R.frame_count(n, N, H)
+    mask = rng.random((B, S, Tn, N // 2)).astype(np.float32)
+    xd, md = dev(T, x), dev(T, mask)
+    feat = ops.stft(xd, N, H)
+    y = ops.mask_istft_feature(feat, md, H)
+    assert y.shape == (B * S, (Tn - 1) * H)
+    ref = R.mask_istft_np(x, mask, N, H).reshape(B * S, -1)
+    assert R.rel_l2(y.cpu().numpy(), ref) < REL_L2
+    # the reversed walk is the same computation item by item: identical bits
+    assert T.equal(ops.mask_istft_feature(feat, md, H, reverse=True), y)
+    # the waveform-fed kernel and the unfused composition agree to float32 rounding
+    y1 = ops.mask_istft(xd, md, N, H)
+    y2 = ops.istft(ops.apply_mask(feat, md), H)
+    assert R.rel_l2(y.cpu().numpy(), y1.cpu().numpy()) < 3e-6
+    assert R.rel_l2(y.cpu().numpy(), y2.cpu().numpy()) < 3e-6
+
+
+@pytest.mark.parametrize("N,H,n,B", [(512, 128, 4797, 3), (512, 256, 6000, 2), (512, 64, 3000, 1), (256, 128, 3000, 3),
+                                     (256, 64, 16000, 2), (1024, 256, 9000, 2), (2048, 512, 9000, 1)])
+@pytest.mark.parametrize("scale", [0.1, 3.0])
+def test_stft_dual_equals_the_two_single_transforms(T, ops, N, H, n, B, scale):
+    rng = np.random.default_rng(N + n)
+    x = dev(T, (rng.standard_normal((B, n)) * scale).astype(np.float32))
+    lin, lg = ops.stft_dual(x, N, H)
+    assert T.equal(lin, ops.stft(x, N, H))
+    if N in (256, 512):
+        assert T.equal(lg, ops.stft_log(x, N, H))          # same kernel body, same bits
+    ref = R.to_log_signal(R.stft_feature_np(x.cpu().numpy(), N, H, np.float64, np.float64))
+    assert R.rel_l2(lg.cpu().numpy(), ref) < REL_L2
+
+
+def test_feature_path_full_size_c2(T, ops):
+    """C2 (256 x 3 s, N = 512, H = 128, S = 3) through stft_dual -> mask_istft_feature: masks that sum to one give the
+    mixture back (>= 100 dB), a sub-batch agrees with the oracle."""
+    N, H, n, B, S = 512, 128, 48000, 256, 3
+    g = T.Generator(device="cuda").manual_seed(1234)
+    x = T.randn(B, n, device="cuda", generator=g) * 0.1
+    lin, lg = ops.stft_dual(x, N, H)
+    m = T.rand(B, S, 376, N // 2, device="cuda", generator=g) + 0.05
+    m = m / m.sum(dim=1, keepdim=True)
+    y = ops.mask_istft_feature(lin, m, H, reverse=True)
+    rec = y.reshape(B, S, -1).sum(dim=1)
+    err = (rec - x).double().pow(2).sum() / x.double().pow(2).sum()
+    assert 10 * np.log10(1.0 / float(err)) >= 100.0
+    sub = slice(101, 103)
+    ref = R.mask_istft_np(x[sub].cpu().numpy(), m[sub].cpu().numpy(), N, H).reshape(2 * S, -1)
+    assert R.rel_l2(y.reshape(B, S, -1)[sub].reshape(2 * S, -1).cpu().numpy(), ref) < REL_L2
+
+
+def test_mask_istft_feature_gradients(T, ops):
+    """differentiable through apply_mask + iSTFT adjoint: compare with autograd of the unfused ops."""
+    N, H, n, B, S = 512, 128, 3000, 2, 3
+    g = T.Generator(device="cuda").manual_seed(5)
+    x = T.randn(B, n, device="cuda", generator=g) * 0.1
+    f = ops.stft(x, N, H).requires_grad_(True)
+    m = T.rand(B, S, f.shape[1], N // 2, device="cuda", generator=g).requires_grad_(True)
+    w = T.randn(B * S, (f.shape[1] - 1) * H, device="cuda", generator=g)
+    (ops.mask_istft_feature(f, m, H) * w).sum().backward()
+    gf, gm = f.grad.clone(), m.grad.clone()
+    f.grad = None; m.grad = None
+    (ops.istft(ops.apply_mask(f, m), H) * w).sum().backward()
+    assert T.allclose(gf, f.grad, rtol=1e-5, atol=1e-7) and T.allclose(gm, m.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_feature_entry_rejects_bad_args(T, ops):
+    f = T.zeros(1, 9, 128, device="cuda")
+    m = T.zeros(1, 1, 9, 64, device="cuda")
+    with pytest.raises(ValueError):
+        ops.mask_istft_feature(f, m, 32)                   # FFT_SIZE 128: no feature-fed kernel
+    f = T.zeros(1, 9, 512, device="cuda")
+    with pytest.raises(AssertionError):
+        ops.mask_istft_feature(f, T.zeros(1, 1, 8, 256, device="cuda"), 128)

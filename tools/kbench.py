@@ -39,6 +39,26 @@ for S in (1, 2, 3, 4):
     timeit(f"mask_istft S={S}", lambda i: ops.mask_istft(waves[i % 3], masks[i % 3], N, H, out=out),
            4 * B * (n + S * T * N // 2 + S * (T - 1) * H))
     del masks
+if N in (256, 512, 1024, 2048, 4096):      # feature-fed synthesis and the dual-output STFT
+    lin = [torch.empty(B, T, N, device=dev) for _ in range(3)]
+    lg = torch.empty(B, T, N, device=dev)
+    timeit("stft_dual", lambda i: ops.stft_dual(waves[i % 3], N, H, out_lin=lin[i % 3], out_log=lg), 4 * B * (n + T * N))
+    for S in (1, 3):
+        masks = [torch.rand(B, S, T, N // 2, device=dev, generator=g) for _ in range(3)]
+        out = torch.empty(B * S, (T - 1) * H, device=dev)
+        for rev in (False, True):
+            timeit(f"mask_istft_feature S={S}{' rev' if rev else ''}", lambda i: ops.mask_istft_feature(lin[i % 3], masks[i % 3], H, out=out, reverse=rev),
+                   4 * B * (n + S * T * N // 2 + S * (T - 1) * H))
+        if S == 3:
+            def step_old(i):
+                ops.stft(waves[i % 3], N, H, log=True); ops.mask_istft(waves[i % 3], masks[i % 3], N, H, out=out)
+            def step_new(i, rev=True):
+                ops.stft_dual(waves[i % 3], N, H, out_lin=lin[i % 3], out_log=lg); ops.mask_istft_feature(lin[i % 3], masks[i % 3], H, out=out, reverse=rev)
+            stepb = 4 * B * (n + T * N) + 4 * B * (n + S * T * N // 2 + S * (T - 1) * H)
+            timeit("STEP stft_log + mask_istft", step_old, stepb)
+            timeit("STEP dual + feature rev", step_new, stepb)
+            timeit("STEP dual + feature fwd", lambda i: step_new(i, False), stepb)
+        del masks
 if "--torch" in sys.argv:   # courtesy baseline: cuFFT through torch.stft / torch.istft on the same GPU
     w_ = torch.hann_window(N, periodic=True, device=dev)
     spec = [torch.stft(w, N, H, window=w_, center=True, pad_mode="constant", return_complex=True) for w in waves]
