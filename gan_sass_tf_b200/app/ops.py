@@ -323,18 +323,21 @@ def stft_dual(wave, fft_size=None, hop=None, out_lin=None, out_log=None):
     return lin, lg
 
 
-def mask_istft_feature(mix_feature, mask, hop=None, out=None, reverse=False):
+def mask_istft_feature(mix_feature, mask, hop=None, out=None, reverse=False, ae_rows=None):
     """Fused ``apply_mask`` + ``istft`` from the mixture's LINEAR packed features ``[B,T,N]`` (what the
     reference's graph holds as ``s_mixed_signals``, main.py:328-337) and ``mask [B,S,T,N/2]`` ->
     ``[B*S, (T-1)*H]``, row ``b*S+s``.  Same results as ``istft(apply_mask(f, m))`` without materialising the
     ``[B*S,T,N]`` product, and as ``mask_istft(wave, m)`` when ``f = stft(wave)``.  ``reverse=True`` walks the rows
     last-to-first (a cache hint when ``mix_feature`` was written just before; results are identical).
+    ``ae_rows`` (float32 ``[B]`` on the device): also receives the per-mixture auto-encoder partial
+    ``sum((sum_s separated_s - mixed)^2)`` of main.py:353-361, computed inside the same kernel (FFT_SIZE 256 / 512,
+    S <= 3 or S = 4 at hop N/4; ``ValueError`` otherwise - use ``ae_loss(apply_mask(...))`` there).
     Differentiable in both arguments."""
     _dev(mix_feature, "mask_istft_feature"); _dev(mask, "mask_istft_feature")
     assert mix_feature.dim() == 3 and mask.dim() == 4, "mask_istft_feature: feature [B,T,N], mask [B,S,T,N/2]"
     N, H = _nh(mix_feature.shape[-1], hop)
     if torch.is_grad_enabled() and (mix_feature.requires_grad or mask.requires_grad):
-        assert out is None, "mask_istft_feature: out= is not supported when gradients are required"
+        assert out is None and ae_rows is None, "mask_istft_feature: out= / ae_rows= are not supported when gradients are required"
         return _Istft.apply(apply_mask(mix_feature, mask), H, False)
     f = _f32c(mix_feature, "mask_istft_feature")
     m = _f32c(mask, "mask_istft_feature")
@@ -346,10 +349,33 @@ def mask_istft_feature(mix_feature, mask, hop=None, out=None, reverse=False):
         out = torch.empty((B * S, L), dtype=torch.float32, device=f.device)
     else:
         assert out.is_cuda and out.dtype == torch.float32 and out.shape == (B * S, L) and out.is_contiguous()
+    if ae_rows is not None:
+        assert ae_rows.is_cuda and ae_rows.dtype == torch.float32 and ae_rows.numel() == B and ae_rows.is_contiguous()
     with torch.cuda.device(f.device):
-        _n.check(_n.lib().gss_mask_istft_feature(f.data_ptr(), m.data_ptr(), B, S, T, N, H,
-                                                 _n.FLAG_REVERSE if reverse else 0, out.data_ptr(), L, _stream()))
+        _n.check(_n.lib().gss_mask_istft_feature_ae(f.data_ptr(), m.data_ptr(), B, S, T, N, H,
+                                                    _n.FLAG_REVERSE if reverse else 0, out.data_ptr(), L,
+                                                    ae_rows.data_ptr() if ae_rows is not None else None, _stream()))
     return out
+
+
+def metric_vector(ae_rows=None, snr=None, elems_per_row=1, out=None):
+    """The per-batch metric vector ``[sum_b mean_i max_k snr[b,i,k], sum_b ae_rows[b] / elems_per_row, 0, B]`` that
+    ``parallel.allreduce_metrics`` sums over the ranks (batch means of main.py:353-361, :446-457), built on the
+    device by one small kernel so that the collective can follow on the same stream."""
+    assert ae_rows is not None or snr is not None, "metric_vector: nothing to reduce"
+    ref = ae_rows if ae_rows is not None else snr
+    _dev(ref, "metric_vector")
+    B = int(ae_rows.numel()) if ae_rows is not None else int(snr.shape[0])
+    m, n = (int(snr.shape[1]), int(snr.shape[2])) if snr is not None else (1, 1)
+    if snr is not None:
+        snr = _f32c(snr, "metric_vector")
+        assert snr.dim() == 3 and snr.shape[0] == B, "metric_vector: snr must be [B, m, n]"
+    vec = torch.empty(4, dtype=torch.float32, device=ref.device) if out is None else out
+    with torch.cuda.device(ref.device):
+        _n.check(_n.lib().gss_metric_finalise(ae_rows.data_ptr() if ae_rows is not None else None,
+                                              snr.data_ptr() if snr is not None else None, B, m, n,
+                                              float(elems_per_row), vec.data_ptr(), _stream()))
+    return vec
 
 
 # ---------------------------------------------------------------------------

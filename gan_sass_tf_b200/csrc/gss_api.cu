@@ -386,9 +386,9 @@ int launch_istft(gss::IstftArgs a, cudaStream_t st) {
 }
 
 // ---- fused synthesis ------------------------------------------------------
-template <int N, int HS, int ST, int WARPS = 4, bool FEAT = false>
+template <int N, int HS, int ST, int WARPS = 4, bool FEAT = false, bool AE = false>
 int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
-    auto k = gss::mask_istft_kernel<N, HS, ST, WARPS, FEAT>;
+    auto k = gss::mask_istft_kernel<N, HS, ST, WARPS, FEAT, AE>;
     constexpr int TEAMS = WARPS * 32 / gss::Geo<N>::TPF;
     size_t smem = gss::SynthSmem<N, ST, FEAT>::bytes(TEAMS);
 #ifdef GSS_TUNE
@@ -501,8 +501,16 @@ int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
 // feature-fed synthesis (gss_mask_istft_feature): same source grouping
 template <int N, int HS>
 int synth_feat_by_s(gss::SynthArgs a, cudaStream_t st) {
+    if (a.ae_rows) {        // fused auto-encoder partial: every source of a mixture in one pass
+        CK(cudaMemsetAsync(a.ae_rows, 0, sizeof(float) * a.B, st));
+        if (a.S == 3) return launch_synth_w<N, HS, 3, 4, true, true>(a, st);
+        if (a.S == 2) return launch_synth_w<N, HS, 2, 4, true, true>(a, st);
+        if (a.S == 1) return launch_synth_w<N, HS, 1, 4, true, true>(a, st);
+        if constexpr (HS == 2) { if (a.S == 4) return launch_synth_w<N, HS, 4, 4, true, true>(a, st); }
+        return fail(GSS_EUNSUPPORTED, "mask_istft_feature: the fused auto-encoder partial needs S <= 3 (S = 4 at hop N/4 only), got S=%d", a.S);
+    }
     if (a.S % 3 == 0) return launch_synth_w<N, HS, 3, 4, true>(a, st);
-    if (a.S % 4 == 0 && HS == 2) return launch_synth_w<N, HS, 4, 4, true>(a, st);
+    if constexpr (HS == 2) { if (a.S % 4 == 0) return launch_synth_w<N, HS, 4, 4, true>(a, st); }
     if (a.S % 2 == 0) return launch_synth_w<N, HS, 2, 4, true>(a, st);
     if (a.S == 1) return launch_synth_w<N, HS, 1, 4, true>(a, st);
     return launch_synth_w<N, HS, 3, 4, true>(a, st);
@@ -565,6 +573,7 @@ int stream512_stft_dual(int hs, gss::StftArgs<float> a, cudaStream_t st) {
 }
 int stream512_synth_feat(int hs, gss::SynthArgs a, cudaStream_t st) {
     if (hs != 2 || a.S != 3) return fail(GSS_EUNSUPPORTED, "GSS_QUICK build: hop N/4, S = 3 only");
+    if (a.ae_rows) { CK(cudaMemsetAsync(a.ae_rows, 0, sizeof(float) * a.B, st)); return launch_synth_w<512, 2, 3, 4, true, true>(a, st); }
     return launch_synth_w<512, 2, 3, 4, true>(a, st);
 }
 #else
@@ -601,6 +610,28 @@ GSS_TEAM_PART(team_hi, GSS_TEAM_DISPATCH_HI)
 #undef GSS_TEAM_PART
 }  // namespace gss_shared
 namespace GSS_NS {
+
+// cluster size for a row reduction: enough CTAs for about two per SM, at most 8 (the portable limit), and a row
+// share of at least ~4 K elements per CTA
+int cluster_for(int64_t rows, int64_t len) {
+    int64_t want = (2 * (int64_t)sm_count() + rows - 1) / (rows < 1 ? 1 : rows);
+    int64_t by_len = len / 4096;
+    if (want > by_len) want = by_len;
+    int cs = 1;
+    while (cs * 2 <= want && cs < 8) cs *= 2;
+    return cs;
+}
+template <typename... KArgs, typename... Args>
+int launch_cluster(void (*kernel)(KArgs...), int64_t rows, int cs, int block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(rows * cs)); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    return GSS_OK;
+}
 
 int grid_for(int64_t work_items, int block) {
     int64_t want = (work_items + block - 1) / block;
@@ -790,6 +821,11 @@ int gss_stft_packed_dual(const float* wave, int64_t B, int64_t n, int64_t ld, in
 
 int gss_mask_istft_feature(const float* feat, const float* mask, int64_t B, int S, int64_t T, int N, int H, int flags,
                            float* out, int64_t ld_out, void* stream) {
+    return gss_mask_istft_feature_ae(feat, mask, B, S, T, N, H, flags, out, ld_out, nullptr, stream);
+}
+
+int gss_mask_istft_feature_ae(const float* feat, const float* mask, int64_t B, int S, int64_t T, int N, int H, int flags,
+                              float* out, int64_t ld_out, float* ae_rows, void* stream) {
     int hs = 0;
     if (int rc = check_nh(N, H, &hs)) return rc;
     if (!feat || !mask || !out) return fail(GSS_EINVAL, "mask_istft_feature: null pointer");
@@ -799,6 +835,7 @@ int gss_mask_istft_feature(const float* feat, const float* mask, int64_t B, int 
     if (ld_out < (T - 1) * H) return fail(GSS_EINVAL, "mask_istft_feature: ld_out=%lld < (T-1)*H=%lld", (long long)ld_out, (long long)((T - 1) * H));
     if (B == 0) return GSS_OK;
     if (!fast_n(N)) {
+        if (ae_rows) return fail(GSS_EUNSUPPORTED, "mask_istft_feature: the fused auto-encoder partial exists for FFT_SIZE 256 / 512 only (got %d)", N);
         if (const int ths = team_hs(N, H)) {
             gss::team::SynthFeatArgs t{};
             t.feat = feat; t.mask = mask; t.out = out; t.B = B; t.T = T; t.ld_out = ld_out; t.S = S;
@@ -810,6 +847,7 @@ int gss_mask_istft_feature(const float* feat, const float* mask, int64_t B, int 
     gss::SynthArgs a{};
     a.feat = feat; a.mask = mask; a.out = out; a.B = B; a.T = T; a.ld_out = ld_out; a.S = S;
     a.rev = (flags & GSS_FLAG_REVERSE) ? 1 : 0;
+    a.ae_rows = ae_rows;
     a.al_in = 1;
     a.al_out = ((uintptr_t)out % 8 == 0) && (ld_out % 2 == 0 || B * S == 1);
     a.npairs = (int)((T + 1) / 2);
@@ -912,7 +950,7 @@ int gss_cross_snr(const float* clear, const float* noisy, int64_t B, int m, int 
     if (!clear || !noisy || !snr) return fail(GSS_EINVAL, "cross_snr: null pointer");
     if (B < 0 || m < 1 || n < 1 || L < 1) return fail(GSS_EINVAL, "cross_snr: bad shape");
     if (B == 0) return GSS_OK;
-    gss::cross_snr_kernel<<<(unsigned)(B * m * n), 256, 0, (cudaStream_t)stream>>>(clear, noisy, m, n, L, eps, snr);
+    if (int rc = launch_cluster(gss::cross_snr_kernel, B * m, cluster_for(B * m, L), 256, (cudaStream_t)stream, clear, noisy, m, n, L, eps, snr)) return rc;
     return after_launch("cross_snr_kernel");
 }
 
@@ -920,15 +958,22 @@ int gss_ae_partial(const float* sep, const float* mix, int64_t B, int S, int64_t
     if (!sep || !mix || !partial) return fail(GSS_EINVAL, "ae_partial: null pointer");
     if (B < 0 || S < 1 || L < 1) return fail(GSS_EINVAL, "ae_partial: bad shape");
     if (B == 0) return GSS_OK;
-    gss::ae_partial_kernel<<<(unsigned)B, 512, 0, (cudaStream_t)stream>>>(sep, mix, S, L, partial);
+    if (int rc = launch_cluster(gss::ae_partial_kernel, B, cluster_for(B, L), 512, (cudaStream_t)stream, sep, mix, S, L, partial)) return rc;
     return after_launch("ae_partial_kernel");
+}
+
+int gss_metric_finalise(const float* ae_rows, const float* snr, int64_t B, int m, int n, double elems_per_row, float* vec4, void* stream) {
+    if (!vec4 || (!ae_rows && !snr)) return fail(GSS_EINVAL, "metric_finalise: null pointer");
+    if (B < 0 || (snr && (m < 1 || n < 1)) || elems_per_row <= 0) return fail(GSS_EINVAL, "metric_finalise: bad shape");
+    gss::metric_finalise_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ae_rows, snr, B, m, n, (float)(1.0 / elems_per_row), vec4);
+    return after_launch("metric_finalise_kernel");
 }
 
 int gss_wav16_normalise(const float* x, int64_t R, int64_t len, int64_t ld, float* minmax, int16_t* pcm, void* stream) {
     if (!x || !minmax || !pcm) return fail(GSS_EINVAL, "wav16: null pointer");
     if (R < 0 || len < 1 || ld < len) return fail(GSS_EINVAL, "wav16: bad shape");
     if (R == 0) return GSS_OK;
-    gss::minmax_kernel<<<(unsigned)R, 512, 0, (cudaStream_t)stream>>>(x, len, ld, minmax);
+    if (int rc = launch_cluster(gss::minmax_kernel, R, cluster_for(R, len), 512, (cudaStream_t)stream, x, len, ld, minmax)) return rc;
     if (int rc = after_launch("minmax_kernel")) return rc;
     gss::wav16_kernel<<<grid_for(R * len, 256), 256, 0, (cudaStream_t)stream>>>(x, R, len, ld, minmax, pcm);
     return after_launch("wav16_kernel");

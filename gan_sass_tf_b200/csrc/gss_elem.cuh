@@ -98,58 +98,144 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return v;
 }
 
-// one CTA per (b, i, k): snr[b,i,k] = c*(ln(mean clear_i^2 + eps) - ln(mean (clear_i - noisy_k)^2 + eps))
+// ---------------------------------------------------------------------------
+// Reductions over long rows (metrics of main.py:353-361 / :446-457, min / max of main.py:112-115).  One thread-block
+// CLUSTER per row: the CTAs of a cluster split the row, reduce their share, and CTA 0 collects the partials of its
+// peers through distributed shared memory - no workspace, no atomics, a deterministic order of additions, and rows x
+// cluster-size CTAs in flight (the reference's defaults give 24 rows: one CTA each would leave 5/6 of the GPU idle).
+// The cluster size is a launch attribute chosen by the host (1 ... 8).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a float of CTA `rank`'s shared memory at the address `p` has in this CTA
+__device__ __forceinline__ float dsmem_ld(const float* p, unsigned rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+constexpr int SNR_KMAX = 8;     // outputs compared per pass over `clear`
+
+// one cluster per (b, i): ONE pass over clear_i computes mean clear_i^2 and mean (clear_i - noisy_k)^2 for every
+// output k (groups of SNR_KMAX), snr[b,i,k] = c*(ln(mean clear_i^2 + eps) - ln(mean (clear_i - noisy_k)^2 + eps))
 __global__ void __launch_bounds__(256) cross_snr_kernel(const float* __restrict__ clear, const float* __restrict__ noisy,
                                                         int m, int n, int64_t L, float eps, float* __restrict__ snr) {
     __shared__ float red[32];
-    const int64_t id = blockIdx.x;
-    const int64_t b = id / (m * n); const int r = (int)(id - b * m * n); const int i = r / n, k = r - i * n;
-    const float* pc = clear + (b * m + i) * L;
-    const float* pn = noisy + (b * n + k) * L;
-    float sp = 0.f, np = 0.f;
-    const bool v4 = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(pc) | reinterpret_cast<uintptr_t>(pn)) & 15) == 0;
-    if (v4) {
-        for (int64_t x = threadIdx.x; x < L / 4; x += blockDim.x) {
-            float4 c4 = __ldg(reinterpret_cast<const float4*>(pc) + x), n4 = __ldg(reinterpret_cast<const float4*>(pn) + x);
-            float d;
-            sp = fmaf(c4.x, c4.x, sp); d = c4.x - n4.x; np = fmaf(d, d, np);
-            sp = fmaf(c4.y, c4.y, sp); d = c4.y - n4.y; np = fmaf(d, d, np);
-            sp = fmaf(c4.z, c4.z, sp); d = c4.z - n4.z; np = fmaf(d, d, np);
-            sp = fmaf(c4.w, c4.w, sp); d = c4.w - n4.w; np = fmaf(d, d, np);
+    __shared__ float part[SNR_KMAX + 1];
+    const unsigned cr = cluster_rank(), cs = cluster_size();
+    const int64_t id = blockIdx.x / cs;                       // (b, i)
+    const int64_t b = id / m;
+    const float* pc = clear + id * L;
+    const bool v4 = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(clear) | reinterpret_cast<uintptr_t>(noisy)) & 15) == 0;
+    for (int k0 = 0; k0 < n; k0 += SNR_KMAX) {
+        const int nk = min(SNR_KMAX, n - k0);
+        const float* pn = noisy + (b * n + k0) * L;
+        float sp = 0.f, np[SNR_KMAX];
+#pragma unroll
+        for (int k = 0; k < SNR_KMAX; ++k) np[k] = 0.f;
+        if (v4) {
+            for (int64_t x = (int64_t)cr * blockDim.x + threadIdx.x; x < L / 4; x += (int64_t)cs * blockDim.x) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(pc) + x);
+                sp = fmaf(c4.x, c4.x, sp); sp = fmaf(c4.y, c4.y, sp); sp = fmaf(c4.z, c4.z, sp); sp = fmaf(c4.w, c4.w, sp);
+#pragma unroll
+                for (int k = 0; k < SNR_KMAX; ++k)
+                    if (k < nk) {
+                        const float4 n4 = __ldg(reinterpret_cast<const float4*>(pn + k * L) + x);
+                        float d;
+                        d = c4.x - n4.x; np[k] = fmaf(d, d, np[k]); d = c4.y - n4.y; np[k] = fmaf(d, d, np[k]);
+                        d = c4.z - n4.z; np[k] = fmaf(d, d, np[k]); d = c4.w - n4.w; np[k] = fmaf(d, d, np[k]);
+                    }
+            }
+        } else {
+            for (int64_t x = (int64_t)cr * blockDim.x + threadIdx.x; x < L; x += (int64_t)cs * blockDim.x) {
+                const float c = __ldg(pc + x);
+                sp = fmaf(c, c, sp);
+#pragma unroll
+                for (int k = 0; k < SNR_KMAX; ++k)
+                    if (k < nk) { const float d = c - __ldg(pn + k * L + x); np[k] = fmaf(d, d, np[k]); }
+            }
         }
-    } else {
-        for (int64_t x = threadIdx.x; x < L; x += blockDim.x) {
-            float c = __ldg(pc + x), d = c - __ldg(pn + x);
-            sp = fmaf(c, c, sp); np = fmaf(d, d, np);
+        sp = block_sum(sp, red);
+        if (threadIdx.x == 0) part[SNR_KMAX] = sp;
+#pragma unroll
+        for (int k = 0; k < SNR_KMAX; ++k)
+            if (k < nk) { const float v = block_sum(np[k], red); if (threadIdx.x == 0) part[k] = v; }
+        cluster_sync_all();                                    // every CTA's partials are in its shared memory
+        if (cr == 0 && threadIdx.x <= nk) {
+            const int slot = threadIdx.x == nk ? SNR_KMAX : threadIdx.x;
+            float v = 0.f;
+            for (unsigned r = 0; r < cs; ++r) v += dsmem_ld(&part[slot], r);
+            part[slot] = v;                                    // only CTA 0 reads its own slots again
         }
+        cluster_sync_all();                                    // peers may overwrite / exit only after CTA 0 has read
+        if (cr == 0 && threadIdx.x < nk)
+            snr[id * n + k0 + threadIdx.x] = 4.342944819f * (logf(part[SNR_KMAX] / (float)L + eps) - logf(part[threadIdx.x] / (float)L + eps));   // app/ops.py:188
+        __syncthreads();
     }
-    sp = block_sum(sp, red);
-    np = block_sum(np, red);
-    if (threadIdx.x == 0)
-        snr[id] = 4.342944819f * (logf(sp / (float)L + eps) - logf(np / (float)L + eps));   // app/ops.py:188
 }
 
-// one CTA per mixture: partial[b] = sum_l (sum_s sep[b,s,l] - mix[b,l])^2
+// one cluster per mixture: partial[b] = sum_l (sum_s sep[b,s,l] - mix[b,l])^2
 __global__ void __launch_bounds__(512) ae_partial_kernel(const float* __restrict__ sep, const float* __restrict__ mix,
                                                          int S, int64_t L, float* __restrict__ partial) {
     __shared__ float red[32];
-    const int64_t b = blockIdx.x;
+    __shared__ float part;
+    const unsigned cr = cluster_rank(), cs = cluster_size();
+    const int64_t b = blockIdx.x / cs;
     float acc = 0.f;
-    for (int64_t x = threadIdx.x; x < L; x += blockDim.x) {
+    for (int64_t x = (int64_t)cr * blockDim.x + threadIdx.x; x < L; x += (int64_t)cs * blockDim.x) {
         float s = -__ldg(mix + b * L + x);
         for (int k = 0; k < S; ++k) s += __ldg(sep + (b * S + k) * L + x);
         acc = fmaf(s, s, acc);
     }
     acc = block_sum(acc, red);
-    if (threadIdx.x == 0) partial[b] = acc;
+    if (threadIdx.x == 0) part = acc;
+    cluster_sync_all();
+    if (cr == 0 && threadIdx.x == 0) {
+        float v = 0.f;
+        for (unsigned r = 0; r < cs; ++r) v += dsmem_ld(&part, r);
+        partial[b] = v;
+    }
+    cluster_sync_all();
 }
 
-// per-row min / max -> minmax[2r], minmax[2r+1]
+// The per-batch metric vector of the multi-GPU all-reduce (app/parallel.py): vec4 = [sum_b mean_i max_k snr[b,i,k],
+// sum_b ae_rows[b] * inv_elems, 0, B] - the batch means of main.py:456-457 and :353-361 are vec4[0] / vec4[3] and
+// vec4[1] / vec4[3] after the sum over ranks.  Either input may be null (its slot is written as 0).  One small CTA.
+__global__ void __launch_bounds__(256) metric_finalise_kernel(const float* __restrict__ ae_rows, const float* __restrict__ snr,
+                                                              int64_t B, int m, int n, float inv_elems, float* __restrict__ vec4) {
+    __shared__ float red[32];
+    float a = 0.f, q = 0.f;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+        if (ae_rows) a += __ldg(ae_rows + b) * inv_elems;
+        if (snr) {
+            float sm = 0.f;
+            for (int i = 0; i < m; ++i) {
+                float best = -INFINITY;
+                for (int k = 0; k < n; ++k) best = fmaxf(best, __ldg(snr + (b * m + i) * n + k));
+                sm += best;
+            }
+            q += sm / (float)m;
+        }
+    }
+    a = block_sum(a, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) { vec4[0] = q; vec4[1] = a; vec4[2] = 0.f; vec4[3] = (float)B; }
+}
+
+// per-row min / max -> minmax[2r], minmax[2r+1]; one cluster per row
 __global__ void __launch_bounds__(512) minmax_kernel(const float* __restrict__ x, int64_t len, int64_t ld, float* __restrict__ minmax) {
     __shared__ float rlo[16], rhi[16];
-    const float* row = x + (int64_t)blockIdx.x * ld;
+    __shared__ float plo, phi;
+    const unsigned cr = cluster_rank(), cs = cluster_size();
+    const int64_t rowi = blockIdx.x / cs;
+    const float* row = x + rowi * ld;
     float lo = INFINITY, hi = -INFINITY;
-    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) { float v = __ldg(row + i); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+    for (int64_t i = (int64_t)cr * blockDim.x + threadIdx.x; i < len; i += (int64_t)cs * blockDim.x) { float v = __ldg(row + i); lo = fminf(lo, v); hi = fmaxf(hi, v); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
     if ((threadIdx.x & 31) == 0) { rlo[threadIdx.x >> 5] = lo; rhi[threadIdx.x >> 5] = hi; }
@@ -159,8 +245,15 @@ __global__ void __launch_bounds__(512) minmax_kernel(const float* __restrict__ x
         hi = threadIdx.x < (blockDim.x >> 5) ? rhi[threadIdx.x] : -INFINITY;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-        if (threadIdx.x == 0) { minmax[2 * blockIdx.x] = lo; minmax[2 * blockIdx.x + 1] = hi; }
+        if (threadIdx.x == 0) { plo = lo; phi = hi; }
     }
+    cluster_sync_all();
+    if (cr == 0 && threadIdx.x == 0) {
+        float l2 = INFINITY, h2 = -INFINITY;
+        for (unsigned r = 0; r < cs; ++r) { l2 = fminf(l2, dsmem_ld(&plo, r)); h2 = fmaxf(h2, dsmem_ld(&phi, r)); }
+        minmax[2 * rowi] = l2; minmax[2 * rowi + 1] = h2;
+    }
+    cluster_sync_all();
 }
 
 // main.py:113-115: d -= min; d *= 32767/(max-min); astype(int16) (truncation), float32 arithmetic

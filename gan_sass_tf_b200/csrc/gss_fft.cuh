@@ -19,6 +19,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// middle-pass twiddles w^1..w^7 kept expanded in registers (16 more registers) instead of being rebuilt from
+// w^1, w^2, w^4 in every transform (16 FP32x2 each): C2 stft_log 64.1 -> 62.4 us, stft_dual 91.1 -> 85.9 us
+// (profiles/r2_variants1.txt); the synthesis kernels measure the same either way.  -DGSS_TW1_FULL=0 restores the rebuild.
+#ifndef GSS_TW1_FULL
+#define GSS_TW1_FULL 1
+#endif
+
 namespace gss {
 
 typedef float2 v2;
@@ -135,6 +142,9 @@ struct TeamCtx {
     float* e1;        // team exchange buffer 1 (re plane, im plane at +E1_PLANE)
     cv2 tw0[8];       // pass-0 twiddles W_N^{(2j+e)*k0}, k0 = 1..7 ([0] unused)
     cv2 tw1[3];       // middle twiddles W_L^{(2q+e)*k1} for k1 = 1, 2, 4, q = j % 4
+#if GSS_TW1_FULL
+    cv2 tw1x[8];      // ... expanded once to k1 = 1..7 (16 more registers, 16 fewer FP32x2 per transform)
+#endif
     unsigned mask;    // lanes of this team inside its warp (all 32 at N = 512, one half at N = 256)
 };
 
@@ -146,6 +156,11 @@ __device__ __forceinline__ void expand_tw(const cv2 (&b)[3], cv2 (&w)[8]) {
     w[6] = cmul<false>(b[1], b[2]);
     w[7] = cmul<false>(w[3], b[2]);
 }
+#if GSS_TW1_FULL
+#define GSS_MID_TW(c, w) const cv2 (&w)[8] = (c).tw1x
+#else
+#define GSS_MID_TW(c, w) cv2 w[8]; expand_tw((c).tw1, w)
+#endif
 
 // teams never span warps (TPF <= 32): a team-scoped __syncwarp keeps the two half-warp teams of N = 256 independent
 template <int N>
@@ -231,6 +246,9 @@ __device__ __forceinline__ void team_init_tab(TeamCtx<N>& c, int j, float* team_
     for (int k0 = 1; k0 < 8; ++k0) { c.tw0[k0].re = lane_tab<N>(TAB_TW0 + 2 * (k0 - 1), j); c.tw0[k0].im = lane_tab<N>(TAB_TW0 + 2 * (k0 - 1) + 1, j); }
 #pragma unroll
     for (int b = 0; b < 3; ++b) { c.tw1[b].re = lane_tab<N>(TAB_TW1 + 2 * b, j); c.tw1[b].im = lane_tab<N>(TAB_TW1 + 2 * b + 1, j); }
+#if GSS_TW1_FULL
+    expand_tw(c.tw1, c.tw1x);
+#endif
 }
 // analysis / synthesis window (scaled) at this lane's sample positions, from the table
 template <int N>
@@ -272,8 +290,7 @@ __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
         float* re1 = re0 + G::P1;
         re0[0] = a[0].re.x; re1[0] = a[0].re.y;
         re0[G::E1_PLANE] = a[0].im.x; re1[G::E1_PLANE] = a[0].im.y;
-        cv2 w[8];
-        expand_tw(c.tw1, w);
+        GSS_MID_TW(c, w);
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) {
             cv2 t = cmul<false>(a[k1], w[k1]);
@@ -341,8 +358,7 @@ __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8], Ho
         const float* re1 = re0 + G::P1;
         a[0].re = make_float2(re0[0], re1[0]);
         a[0].im = make_float2(re0[G::E1_PLANE], re1[G::E1_PLANE]);
-        cv2 w[8];
-        expand_tw(c.tw1, w);
+        GSS_MID_TW(c, w);
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) {
             cv2 t;

@@ -664,6 +664,7 @@ struct SynthArgs {
     const float* wave; const float* mask; float* out;
     const float* feat;              // FEAT kernels: linear packed mixture spectrum [B, T, N] instead of `wave`
     int rev;                        // FEAT kernels: walk the work items from the last row to the first
+    float* ae_rows;                 // AE kernels: [B] sums of ((sum_s mask_s - 1) * feature)^2 over the row's packed elements
     long long* timing;              // [items][8] cycle accumulators (GSS_TIMING builds only)
     int64_t B, n, ld, T, ld_out;
     int S, ngroups;                 // ngroups = ceil(S / ST)
@@ -714,7 +715,10 @@ __device__ __forceinline__ void mask_pack_pair(const PairSpec& x, const v2 (&ga)
 // FEAT = true (gss_mask_istft_feature): the mixture's LINEAR packed spectrum [B, T, N] is read back (one 1-D TMA bulk
 // copy of the pair's two feature rows per iteration) instead of being recomputed from the waveform: one of the
 // 1 + ST transforms per pair goes away (the kernel is bound by issue slots, not by bytes), for 4TN - 4n more bytes.
-template <int N, int HS, int ST, int WARPS, bool FEAT = false>
+// AE = true: the auto-encoder loss partial of main.py:353-361 for a mask separator, sum((sum_s separated_s - mixed)^2) =
+// sum(((sum_s mask_s - 1) * feature)^2) over the packed elements, accumulated from the registers that already hold the
+// pair's spectrum and gains (needs every source in one pass: S <= ST) and added to p.ae_rows[b] once per work item.
+template <int N, int HS, int ST, int WARPS, bool FEAT = false, bool AE = false>
 __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((65536 / (WARPS * 32)) / 8) * 8) mask_istft_kernel(const SynthArgs p) {
     typedef SGeo<N, HS> SG; typedef Geo<N> G; typedef SynthSmem<N, ST, FEAT> SM;
     constexpr int NH = N / 2;
@@ -826,6 +830,7 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
 #ifdef GSS_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
+    v2 ae_acc = make_float2(0.f, 0.f);
     auto step = [&](int q, auto tag) {
         constexpr bool FAST = decltype(tag)::value;
         GSS_T(7);
@@ -866,6 +871,11 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
         const float* ma = mA + stg * SM::STAGE_FLOATS;
         const float* mb = mB + stg * SM::STAGE_FLOATS;
         const bool own = FAST || q >= q0;
+        v2 gsa[AE ? 4 : 1], gsb[AE ? 4 : 1];          // AE: sum of the sources' gains minus one, per bin
+        if constexpr (AE) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { gsa[i] = vset(-1.f); gsb[i] = vset(-1.f); }
+        }
         // one source: masks -> inverse transform -> overlap-add -> finished slots to global memory.
         // `as` = accumulator set (static), `s` = source index (static when the loop is unrolled)
         auto source = [&](auto as_c, int s) {
@@ -875,6 +885,10 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
             for (int i = 0; i < 4; ++i) {
                 ga[i] = make_float2(ma[s * 2 * NH + SG::L * i], mb[s * 2 * NH + SG::L * i]);
                 gb[i] = hb ? make_float2(ma[s * 2 * NH + NH + SG::L * i], mb[s * 2 * NH + NH + SG::L * i]) : make_float2(0.f, 0.f);
+            }
+            if constexpr (AE) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { gsa[i] = vadd(gsa[i], ga[i]); gsb[i] = vadd(gsb[i], gb[i]); }
             }
             cv2 a[8];
             mask_pack_pair<N>(x, ga, gb, t0, a);
@@ -929,6 +943,21 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
             if (ST > 2 && (FAST || 2 < ns)) source(std::integral_constant<int, (ST > 2 ? 2 : 0)>(), 2);
             if (ST > 3 && (FAST || 3 < ns)) source(std::integral_constant<int, (ST > 3 ? 3 : 0)>(), 3);
         }
+        if constexpr (AE) {
+            if (own) {            // halo pairs belong to the neighbouring work item
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const v2 ea = vfma(x.ar[i], x.ar[i], vmul(x.ai[i], x.ai[i]));
+                    const v2 da = vmul(gsa[i], gsa[i]);
+                    ae_acc = vfma(da, ea, ae_acc);
+                    if (hb) {     // an absent frame b has no elements (its gains are not read)
+                        const v2 eb = vfma(x.br[i], x.br[i], vmul(x.bi[i], x.bi[i]));
+                        const v2 db = vmul(gsb[i], gsb[i]);
+                        ae_acc = vfma(db, eb, ae_acc);
+                    }
+                }
+            }
+        }
         base += SG::ADV;
         wptr += SG::ADV * SG::L;
         optr += SG::ADV * SG::L;
@@ -952,6 +981,12 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(WARPS <= 4 ? 255 : ((6
 #pragma unroll
                 for (int i = 0; i < SG::KEEP; ++i) o.write(orow0 + s * p.ld_out, base + i, i % HS, acc[s][i], false);
             }
+    }
+    if constexpr (AE) {
+        float e = ae_acc.x + ae_acc.y;
+#pragma unroll
+        for (int d = G::TPF / 2; d >= 1; d >>= 1) e += __shfl_xor_sync(ctx.mask, e, d);
+        if (j == 0) atomicAdd(p.ae_rows + b, e);
     }
 #ifdef GSS_TIMING
     if (j == 0 && p.timing) {

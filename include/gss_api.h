@@ -112,6 +112,21 @@ int gss_stft_packed_dual(const float* wave, int64_t B, int64_t n, int64_t ld, in
 int gss_mask_istft_feature(const float* feat, const float* mask, int64_t B, int S, int64_t T, int N, int H, int flags,
                            float* out, int64_t ld_out, void* stream);
 
+/* Same, and the auto-encoder loss partial of main.py:353-361 from the registers that already hold the spectrum and the
+ * gains: ae_rows[b] = sum over the packed elements of mixture b of ((sum_s mask_s - 1) * feature)^2, i.e.
+ * sum((sum_s separated_s - mixed)^2) for separated_s = mask_s * mixed; the loss is sum_b ae_rows[b] / (B*T*N).
+ * ae_rows [B] f32 is zeroed by the call (a memset node on `stream`).  FFT_SIZE 256 / 512 and S <= 3 (S = 4 at hop
+ * N/4); other shapes return GSS_EUNSUPPORTED (use gss_apply_mask + gss_ae_partial).  ae_rows = NULL: plain call. */
+int gss_mask_istft_feature_ae(const float* feat, const float* mask, int64_t B, int S, int64_t T, int N, int H, int flags,
+                              float* out, int64_t ld_out, float* ae_rows, void* stream);
+
+/* The per-batch metric vector that is all-reduced over the GPUs (app/parallel.py; batch means of main.py:353-361 and
+ * :446-457): vec4 = [sum_b mean_i max_k snr[b,i,k], sum_b ae_rows[b] / elems_per_row, 0, B].  snr [B,m,n] (from
+ * gss_cross_snr) and ae_rows [B] (from gss_mask_istft_feature_ae or gss_ae_partial) may each be NULL.  One tiny launch,
+ * so the all-reduce can follow on the same stream without a host round trip. */
+int gss_metric_finalise(const float* ae_rows, const float* snr, int64_t B, int m, int n, double elems_per_row,
+                        float* vec4, void* stream);
+
 /* A7 alone on packed features: mix [B,T,N], mask [B,S,T,N/2] -> out [B*S,T,N] */
 int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_t T, int N,
                    float* out, void* stream);

@@ -115,3 +115,55 @@ def test_feature_entry_rejects_bad_args(T, ops):
     f = T.zeros(1, 9, 512, device="cuda")
     with pytest.raises(AssertionError):
         ops.mask_istft_feature(f, T.zeros(1, 1, 8, 256, device="cuda"), 128)
+
+
+@pytest.mark.parametrize("N,H,n,B,S", [(512, 128, 9000, 3, 3), (512, 128, 48000, 2, 3), (512, 256, 5000, 2, 2), (512, 64, 4000, 1, 1),
+                                       (512, 128, 6001, 2, 4), (256, 128, 5000, 4, 3), (256, 64, 3000, 2, 4)])
+def test_fused_autoencoder_partial(T, ops, N, H, n, B, S):
+    """ae_rows from inside the synthesis kernel == main.py:353-361 on the masked features (oracle: NumPy float64)."""
+    rng = np.random.default_rng(N + n + S)
+    x = (rng.standard_normal((B, n)) * 0.1).astype(np.float32)
+    Tn, _ = R.frame_count(n, N, H)
+    mask = rng.random((B, S, Tn, N // 2)).astype(np.float32)
+    feat = ops.stft(dev(T, x), N, H)
+    rows = T.full((B,), 7.0, device="cuda")                      # the call zeroes it
+    y = ops.mask_istft_feature(feat, dev(T, mask), H, ae_rows=rows)
+    assert T.equal(y, ops.mask_istft_feature(feat, dev(T, mask), H))       # the extra output does not change the waveforms
+    f64 = feat.cpu().numpy().astype(np.float64)
+    sep = R.apply_mask(f64, mask.astype(np.float64)).reshape(B, S, Tn, N)
+    ref_rows = ((sep.sum(axis=1) - f64) ** 2).sum(axis=(1, 2))
+    np.testing.assert_allclose(rows.cpu().numpy(), ref_rows, rtol=2e-5)
+    # the reference's scalar: mean over every element (R.ae_loss restates main.py:353-361)
+    vec = ops.metric_vector(ae_rows=rows, elems_per_row=Tn * N).cpu().numpy()
+    assert vec[3] == B and vec[2] == 0 and vec[0] == 0
+    assert abs(vec[1] / B - R.autoencoder_loss(sep.reshape(B * S, Tn, N), f64, B, S)) <= 2e-5 * abs(vec[1] / B)
+
+
+def test_fused_autoencoder_partial_unsupported_shapes(T, ops):
+    f = T.zeros(1, 9, 512, device="cuda")
+    rows = T.zeros(1, device="cuda")
+    with pytest.raises(ValueError):
+        ops.mask_istft_feature(f, T.zeros(1, 5, 9, 256, device="cuda"), 128, ae_rows=rows)     # S = 5 needs two passes
+    f = T.zeros(1, 9, 1024, device="cuda")
+    with pytest.raises(ValueError):
+        ops.mask_istft_feature(f, T.zeros(1, 3, 9, 512, device="cuda"), 256, ae_rows=rows)     # team kernels: no fused partial
+
+
+@pytest.mark.parametrize("B,m,n,L", [(8, 3, 4, 128 * 256), (2, 2, 3, 48000), (1, 1, 1, 1001), (3, 2, 11, 5000), (40, 3, 4, 376 * 512)])
+def test_cluster_reductions_match_oracle(T, ops, B, m, n, L):
+    """cross-SNR (one pass over `clear` for all outputs, cluster reduction), AE partial, min / max, metric vector."""
+    rng = np.random.default_rng(B * 1000 + L)
+    clear = rng.standard_normal((B, m, L)).astype(np.float32)
+    noisy = (clear[:, :1].repeat(n, axis=1) + 0.3 * rng.standard_normal((B, n, L))).astype(np.float32)
+    snr = ops.batch_cross_snr(dev(T, clear), dev(T, noisy))
+    ref = R.batch_cross_snr(clear.astype(np.float64), noisy.astype(np.float64))
+    np.testing.assert_allclose(snr.cpu().numpy(), ref, atol=2e-3)
+    vec = ops.metric_vector(snr=snr).cpu().numpy()
+    assert abs(vec[0] / B - ref.max(axis=2).mean()) < 2e-3 and vec[3] == B
+    mix = rng.standard_normal((B, L)).astype(np.float32)
+    ae = float(ops.ae_loss(dev(T, noisy.reshape(B * n, 1, L)), dev(T, mix.reshape(B, 1, L)), n))
+    ref_ae = float(np.mean((noisy.astype(np.float64).sum(axis=1) - mix.astype(np.float64)) ** 2))
+    assert abs(ae - ref_ae) <= 1e-4 * abs(ref_ae)
+    pcm = ops.wav16_normalise(dev(T, clear.reshape(B * m, L))).cpu().numpy()
+    refp = np.stack([R.wav16_normalise(r) for r in clear.reshape(B * m, L)])
+    assert np.abs(pcm.astype(np.int32) - refp.astype(np.int32)).max() <= 1

@@ -41,6 +41,13 @@ if "--istft" in sys.argv:
     t_ie = timeit(lambda i: ops.istft(feats[i % 3], H, exp=True))
     y = ops.istft(feats[0], H)
     print(f"{tag:24s} istft {t_i:7.1f} us  istft_exp {t_ie:7.1f} us | fp {y.double().abs().sum().item():.6f}")
+if "--feat" in sys.argv:
+    lins = [ops.stft(w, N, H) for w in waves]
+    lg = torch.empty_like(lins[0])
+    t_d = timeit(lambda i: ops.stft_dual(waves[i % 3], N, H, out_lin=lins[i % 3], out_log=lg))
+    t_f = timeit(lambda i: ops.mask_istft_feature(lins[i % 3], masks[i % 3], H, out=out))
+    ops.mask_istft_feature(lins[0], masks[0], H, out=out)
+    print(f"{tag:24s} {extra:28s} stft_dual {t_d:7.1f} us  mask_istft_feature {t_f:7.1f} us | fp out {out.double().abs().sum().item():.6f}")
 ops.mask_istft(waves[0], masks[0], N, H, out=out)
 f = ops.stft_log(waves[0], N, H)
 print(f"{tag:24s} {extra:28s} stft_log {t_st:7.1f} us  mask_istft {t_sy:7.1f} us  | fp out {out.double().abs().sum().item():.6f} feat {f.double().abs().sum().item():.6f}")
