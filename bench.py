@@ -317,7 +317,8 @@ def run_native(args):
             pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
         except Exception:
             pass
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     _native.lib()
 
     def barrier():
@@ -371,8 +372,10 @@ def run_native(args):
     # ---- sustained: the same step back to back for >= 2 s, with its own clocks record ------------------
     sustained = None
     if not args.no_sustained:
-        per = total_ms / args.steps
-        ns = int(2200.0 / max(per, 1e-3)) + 1
+        tper = torch.tensor([total_ms / args.steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tper, op=dist.ReduceOp.MAX)      # every rank must run the same number of steps (one collective each)
+        ns = int(2200.0 / max(float(tper[0]), 1e-3)) + 1
         s_ms, _, _, _, (s0, s1) = timed(primary, ns, 3, per_kernel=False)
         sustained = {"steps": ns, "seconds": s_ms * 1e-3, "ms_per_step": s_ms / ns, "clocks": sampler.window(s0, s1) if sampler else None}
 
