@@ -23,8 +23,6 @@ SIGNATURES = {
     "gss_version": (c_int, []),
     "gss_last_error": (c_char_p, []),
     "gss_launch_count": (c_int64, []),
-    "gss_set_path": (c_int, [c_int]),
-    "gss_set_synth_variant": (c_int, [c_int]),
     "gss_supported_fft_sizes": (c_int, [POINTER(c_int), c_int]),
     "gss_frame_count": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "gss_stft_packed": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P, _P]),
@@ -35,6 +33,7 @@ SIGNATURES = {
     "gss_mask_istft_feature": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, c_int, _P, c_int64, _P]),
     "gss_mask_istft_feature_ae": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, c_int, _P, c_int64, _P, _P]),
     "gss_metric_finalise": (c_int, [_P, _P, c_int64, c_int, c_int, ctypes.c_double, _P, _P]),
+    "gss_gather_rows_i16": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P]),
     "gss_apply_mask": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P]),
     "gss_ola_norm_scale": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P]),
     "gss_scale_packed": (c_int, [_P, _P, c_int64, c_int, c_float, c_float, _P]),
@@ -58,7 +57,15 @@ SIGNATURES = {
     "gss_apply_mask_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P]),
 }
 
+# only in lib/libgss_experimental.so (include/gss_api.h under GSS_EXPERIMENTAL): process-wide kernel-family switches
+EXPERIMENTAL_SIGNATURES = {
+    "gss_set_path": (c_int, [c_int]),
+    "gss_set_synth_variant": (c_int, [c_int]),
+}
+EXPERIMENTAL_LIB_PATH = os.path.join(_HERE, "lib", "libgss_experimental.so")
+
 _lib = None
+_product_lib = None
 
 
 class GssError(RuntimeError):
@@ -106,14 +113,47 @@ def supported_fft_sizes():
     return tuple(buf[i] for i in range(min(k, 16)))
 
 
+def load_experimental():
+    """Switch this process to ``lib/libgss_experimental.so`` (a superset of the product ABI: the measured-slower
+    synthesis variants, the team kernels at 256 / 512 and the switches below).  For the cross-check tests and the
+    tuning tools; ``unload_experimental()`` goes back to the product library."""
+    global _lib, _product_lib
+    if not os.path.exists(EXPERIMENTAL_LIB_PATH):
+        raise ImportError(f"{EXPERIMENTAL_LIB_PATH} is missing: build it with `python -m gan_sass_tf_b200.build`")
+    if _product_lib is None:
+        _product_lib = lib()
+    h = ctypes.CDLL(EXPERIMENTAL_LIB_PATH)
+    for name, (res, args) in {**SIGNATURES, **EXPERIMENTAL_SIGNATURES}.items():
+        fn = getattr(h, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = h
+    return h
+
+
+def unload_experimental():
+    global _lib
+    if _product_lib is not None:
+        _lib = _product_lib
+
+
+def _experimental():
+    h = lib()
+    if not hasattr(h, "gss_set_path"):
+        raise RuntimeError("kernel-family switches exist in lib/libgss_experimental.so only: call _native.load_experimental() first")
+    return h
+
+
 def set_path(path: int):
-    """0 = automatic kernel selection, 1 = no register-exchange kernels (team kernels), 2 = per-frame kernels only."""
-    check(lib().gss_set_path(path))
+    """0 = automatic kernel selection, 1 = no register-exchange kernels (team kernels), 2 = per-frame kernels only.
+    Experimental library only."""
+    check(_experimental().gss_set_path(path))
 
 
 def set_synth_variant(variant: int):
-    """N = 512 fused synthesis: 0 = register-resident kernel, 1 = role-split CTAs, 2 = tensor-memory state."""
-    check(lib().gss_set_synth_variant(variant))
+    """N = 512 fused synthesis: 0 = register-resident kernel, 1 = role-split CTAs, 2 = tensor-memory state.
+    Experimental library only."""
+    check(_experimental().gss_set_synth_variant(variant))
 
 
 def launch_count() -> int:

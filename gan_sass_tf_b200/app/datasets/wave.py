@@ -19,7 +19,11 @@ import numpy as np
 import torch
 from scipy.signal import lfilter
 
+import glob
+import os
+
 from .. import hparams, ops
+from ... import _native as _n
 from .dataset import Dataset
 
 
@@ -30,6 +34,7 @@ class WaveformData(Dataset):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.seed = seed
         self.subset = {}
+        self.n_epochs = 0          # advances the shuffle seed: every epoch gets its own order
 
     def add_subset(self, name, waves):
         """``waves``: list of 1-D int16 (or float in [-1, 1), scaled to int16) arrays at 16 kHz."""
@@ -45,8 +50,29 @@ class WaveformData(Dataset):
         lengths = np.asarray([len(pcm[i]) for i in order], dtype=np.int64)
         offsets = np.concatenate([[0], np.cumsum(lengths)])
         flat = torch.from_numpy(np.concatenate([pcm[i] for i in order])).to(self.device)
-        self.subset[name] = (flat, offsets, lengths)
+        self.subset[name] = (flat, offsets, lengths,
+                             torch.from_numpy(offsets[:-1].astype(np.int64)).to(self.device), torch.from_numpy(lengths).to(self.device))
         self.is_loaded = True
+
+    def add_directory(self, name, path, pattern="**/*.wav", skip_prefixes=("sa",)):
+        """File-backed corpus: every 16 kHz mono WAV under ``path`` becomes an utterance of subset ``name`` - the
+        per-file loop of ``TIMIT/process.py:89-110`` (which skips the dialect sentences ``sa*`` and raises on any other
+        sampling rate, process.py:90-96) without its STFT: the waveforms are stored, the transform runs per batch."""
+        import scipy.io.wavfile
+        waves = []
+        for fname in sorted(glob.glob(os.path.join(path, pattern), recursive=True)):
+            if os.path.basename(fname).lower().startswith(tuple(skip_prefixes)):
+                continue
+            rate, w = scipy.io.wavfile.read(fname)
+            if rate != hparams.SAMPLE_RATE:
+                raise ValueError('Sampling rate of "%s" is %d, must be %d' % (fname, rate, hparams.SAMPLE_RATE))   # process.py:95-96
+            if w.ndim != 1:
+                w = w.reshape(w.shape[0], -1)[:, 0]
+            waves.append(w)
+        if not waves:
+            raise FileNotFoundError('no WAV files matching "%s" under "%s"' % (pattern, path))
+        self.add_subset(name, waves)
+        return len(waves)
 
     def install_and_load(self):
         """Synthetic stand-in corpus (no TIMIT in this environment): 2 x 64 utterances of
@@ -67,17 +93,21 @@ class WaveformData(Dataset):
             raise RuntimeError('Dataset is not loaded.')
         if subset not in self.subset:
             raise KeyError('Unknown subset "%s", valid options are %s' % (subset, list(self.subset.keys())))
-        flat, offsets, lengths = self.subset[subset]
+        flat, offsets, lengths, offsets_d, lengths_d = self.subset[subset]
         N, H = hparams.FFT_SIZE, hparams.hop_size()
         nb = (len(lengths) + batch_size - 1) // batch_size
-        order = np.random.default_rng(self.seed).permutation(nb) if shuffle else np.arange(nb)
+        order = np.random.default_rng([self.seed, self.n_epochs]).permutation(nb) if shuffle else np.arange(nb)
+        self.n_epochs += 1
         for bi in order:
             lo = bi * batch_size
             idx = np.arange(lo, lo + batch_size) % len(lengths)          # the last batch wraps (timit.py:74 re-uses the tail)
             n_max = max(int(lengths[idx].max()), N)
-            batch = torch.zeros((batch_size, n_max), dtype=torch.int16, device=self.device)
-            for r, i in enumerate(idx):
-                batch[r, :lengths[i]] = flat[offsets[i]:offsets[i + 1]]
+            n_max += n_max % 2                                           # even rows: aligned 2-sample loads in the transform
+            batch = torch.empty((batch_size, n_max), dtype=torch.int16, device=self.device)
+            idx_d = torch.from_numpy(idx.astype(np.int64)).to(self.device, non_blocking=True)
+            with torch.cuda.device(self.device):                         # one gather launch instead of a per-row copy loop
+                _n.check(_n.lib().gss_gather_rows_i16(flat.data_ptr(), offsets_d.data_ptr(), lengths_d.data_ptr(), idx_d.data_ptr(),
+                                                      batch_size, n_max, batch.data_ptr(), torch.cuda.current_stream().cuda_stream))
             feats = ops.stft(batch, N, H)
             frames = torch.as_tensor((lengths[idx] + ((-lengths[idx]) % H) % N) // H + 1)
             yield feats, frames

@@ -19,6 +19,8 @@ mask-emitting separator, which the reference only has as a stub
 """
 from __future__ import annotations
 
+import zlib
+
 import torch
 
 from . import hparams
@@ -74,7 +76,8 @@ class _Params:
 
     def linear(self, key, n_in, n_out, device, bias=True):
         if key not in self.layers:
-            g = torch.Generator().manual_seed(abs(hash(key)) % (2 ** 31))
+            # a stable hash: Python salts str hashes per process, which made the "seeded" weights differ between runs and ranks
+            g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * int(getattr(hparams, 'SEED', 0))) % (2 ** 31))
             lin = torch.nn.Linear(n_in, n_out, bias=bias)
             with torch.no_grad():
                 lin.weight.copy_(torch.randn(n_out, n_in, generator=g) * (1.0 / n_in) ** 0.5)

@@ -13,8 +13,14 @@
 #include "../../include/gss_api.h"
 #include "gss_stream.cuh"
 #include "gss_team.cuh"
+// GSS_EXPERIMENTAL (lib/libgss_experimental.so, built beside the product library and loaded only by the tests and the
+// tuning tools): the two measured-slower N = 512 synthesis variants (role-split CTAs, tensor-memory-parked state) and the
+// process-wide switches gss_set_path / gss_set_synth_variant that pick kernel families.  The product library has no
+// mutable global state beyond the per-device constant tables and copy-stream sets.
+#ifdef GSS_EXPERIMENTAL
 #include "gss_split.cuh"
 #include "gss_tmem.cuh"
+#endif
 
 // The library is one source compiled in several parts (GSS_PART = 0..4, see gan_sass_tf_b200/build.py) so that
 // the ~170 kernel instances build in parallel: part 0 = the C ABI, element-wise kernels, copy pipelines and the
@@ -292,12 +298,19 @@ int team_synth_feat(gss::team::SynthFeatArgs a, cudaStream_t st) {
     return team_synth_feat_st<N, HS, 3>(a, st);
 }
 // F<N, HS>::run(args...) for the (N, hs) pairs the team kernels cover
+#ifdef GSS_EXPERIMENTAL     // team kernels at 256 / 512 are reachable through gss_set_path(1) only: cross-check builds
 #define GSS_TEAM_DISPATCH_LO(N, hs, CALL)                                                                           \
     do {                                                                                                            \
         if (N == 256 && hs == 1) { CALL(256, 1) } if (N == 256 && hs == 2) { CALL(256, 2) } if (N == 256 && hs == 4) { CALL(256, 4) }       \
         if (N == 512 && hs == 1) { CALL(512, 1) } if (N == 512 && hs == 2) { CALL(512, 2) } if (N == 512 && hs == 4) { CALL(512, 4) }       \
         if (N == 1024 && hs == 2) { CALL(1024, 2) } if (N == 1024 && hs == 4) { CALL(1024, 4) } if (N == 1024 && hs == 8) { CALL(1024, 8) } \
     } while (0)
+#else
+#define GSS_TEAM_DISPATCH_LO(N, hs, CALL)                                                                           \
+    do {                                                                                                            \
+        if (N == 1024 && hs == 2) { CALL(1024, 2) } if (N == 1024 && hs == 4) { CALL(1024, 4) } if (N == 1024 && hs == 8) { CALL(1024, 8) } \
+    } while (0)
+#endif
 #define GSS_TEAM_DISPATCH_HI(N, hs, CALL)                                                                           \
     do {                                                                                                            \
         if (N == 2048 && hs == 2) { CALL(2048, 2) } if (N == 2048 && hs == 4) { CALL(2048, 4) } if (N == 2048 && hs == 8) { CALL(2048, 8) } \
@@ -439,6 +452,7 @@ int launch_synth(gss::SynthArgs a, cudaStream_t st) {
 #endif
     return launch_synth_w<N, HS, ST, 4>(a, st);
 }
+#ifdef GSS_EXPERIMENTAL
 // role-split variant (gss_split.cuh): one CTA of 1 + ST warps per (row, source group, chunk)
 template <int N, int HS, int ST>
 int launch_synth_split(gss::SynthArgs a, cudaStream_t st) {
@@ -478,9 +492,11 @@ int synth_variant() {       // 0 = one warp per pair (gss_stream.cuh), 1 = role-
     if (v < 0) { const char* e = getenv("GSS_SYNTH_SPLIT"); v = e ? atoi(e) : 0; if (v < 0 || v > 2) v = 0; g_synth_variant.store(v); }
     return v;
 }
+#endif  // GSS_EXPERIMENTAL
 
 template <int N, int HS>
 int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
+#ifdef GSS_EXPERIMENTAL
     if constexpr (N == 512) {
         if (synth_variant() == 1) {
             if (a.S % 3 == 0) return launch_synth_split<N, HS, 3>(a, st);
@@ -490,6 +506,7 @@ int synth_by_s(gss::SynthArgs a, cudaStream_t st) {
         }
         if (synth_variant() == 2 && a.S % 3 == 0) return launch_synth_tm<N, HS, 3>(a, st);   // other S: default kernel
     }
+#endif
     // sources carried per pass: 3 when S is a multiple of 3, else 2 (S even) or 1
     if (a.S % 3 == 0) return launch_synth<N, HS, 3>(a, st);
     if (a.S % 4 == 0 && HS == 2) return launch_synth<N, HS, 4>(a, st);
@@ -564,7 +581,9 @@ int stream512_istft(int hs, bool ex, gss::IstftArgs a, cudaStream_t st) {
 }
 int stream512_synth(int hs, gss::SynthArgs a, cudaStream_t st) {
     if (hs != 2 || a.S != 3) return fail(GSS_EUNSUPPORTED, "GSS_QUICK build: hop N/4, S = 3 only");
+#ifdef GSS_EXPERIMENTAL
     if (synth_variant() == 2) return launch_synth_tm<512, 2, 3>(a, st);
+#endif
     return launch_synth<512, 2, 3>(a, st);
 }
 int stream512_stft_dual(int hs, gss::StftArgs<float> a, cudaStream_t st) {
@@ -651,8 +670,17 @@ struct Workspace {
         cap = bytes; return GSS_OK;
     }
 };
-std::mutex g_ws_mu;
-Workspace g_ws_in, g_ws_out;
+// one workspace pair, one private (non-blocking) stream and one mutex per device ordinal: a call on device 1 never
+// touches device 0's buffers, and the *_host entry points do not serialise the device through the legacy stream
+struct HostWs { std::mutex mu; Workspace in, out; cudaStream_t st = nullptr; };
+HostWs g_host_ws[64];
+int host_ws(HostWs** out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(GSS_EUNSUPPORTED, "device ordinal %d out of range", dev);
+    *out = &g_host_ws[dev];
+    return GSS_OK;
+}
 
 // Copy engines of the host-buffer pipelines.  One H2D and one D2H stream per host thread, so that
 // uploads of batch k+1 and downloads of batch k use both directions of the link at once.
@@ -661,6 +689,7 @@ Workspace g_ws_in, g_ws_out;
 struct CopyStreams {
     static constexpr int NTAG = 8;
     struct Tag { const void* key = nullptr; cudaEvent_t ev = nullptr; };
+    std::mutex mu;                  // held while a call enqueues on this device's copy streams / edits the tags
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t order = nullptr;
@@ -693,7 +722,22 @@ struct CopyStreams {
         return GSS_OK;
     }
 };
-thread_local CopyStreams g_cs;
+// One set per DEVICE (not per thread): streams and events belong to the device that was current when they were
+// created, and a download may be waited for by a thread other than the one that enqueued it.
+CopyStreams g_cs_dev[64];
+int copy_streams(CopyStreams** out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(GSS_EUNSUPPORTED, "device ordinal %d out of range", dev);
+    *out = &g_cs_dev[dev];
+    return GSS_OK;
+}
+#define GSS_CS_LOCKED(cs)                                   \
+    CopyStreams* cs##_p = nullptr;                          \
+    if (int rc_ = copy_streams(&cs##_p)) return rc_;        \
+    CopyStreams& cs = *cs##_p;                              \
+    std::lock_guard<std::mutex> cs##_lk(cs.mu);             \
+    if (int rc_ = cs.init()) return rc_
 
 }  // namespace GSS_NS
 
@@ -704,6 +748,7 @@ extern "C" {
 int gss_version(void) { return 100; }
 const char* gss_last_error(void) { return g_err.c_str(); }
 int64_t gss_launch_count(void) { return g_launches.load(); }
+#ifdef GSS_EXPERIMENTAL
 int gss_set_path(int path) {
     if (path < 0 || path > 2) return fail(GSS_EINVAL, "set_path: 0 = automatic, 1 = no register-exchange kernels, 2 = gss_generic.cuh only");
     g_force_generic.store(path);
@@ -714,6 +759,7 @@ int gss_set_synth_variant(int variant) {
     g_synth_variant.store(variant);
     return GSS_OK;
 }
+#endif  // GSS_EXPERIMENTAL
 int gss_supported_fft_sizes(int* sizes, int cap) {
     int k = 0;
     for (int N = 16; N <= 65536; N *= 2)
@@ -969,6 +1015,15 @@ int gss_metric_finalise(const float* ae_rows, const float* snr, int64_t B, int m
     return after_launch("metric_finalise_kernel");
 }
 
+int gss_gather_rows_i16(const int16_t* flat, const int64_t* offsets, const int64_t* lengths, const int64_t* idx,
+                        int64_t B, int64_t ld, int16_t* out, void* stream) {
+    if (!flat || !offsets || !lengths || !idx || !out) return fail(GSS_EINVAL, "gather_rows_i16: null pointer");
+    if (B < 0 || ld < 1) return fail(GSS_EINVAL, "gather_rows_i16: bad shape");
+    if (B == 0) return GSS_OK;
+    gss::gather_rows_i16_kernel<<<grid_for(B * ld, 256), 256, 0, (cudaStream_t)stream>>>(flat, offsets, lengths, idx, B, ld, out);
+    return after_launch("gather_rows_i16_kernel");
+}
+
 int gss_wav16_normalise(const float* x, int64_t R, int64_t len, int64_t ld, float* minmax, int16_t* pcm, void* stream) {
     if (!x || !minmax || !pcm) return fail(GSS_EINVAL, "wav16: null pointer");
     if (R < 0 || len < 1 || ld < len) return fail(GSS_EINVAL, "wav16: bad shape");
@@ -985,14 +1040,17 @@ int gss_stft_packed_host(const float* wave_h, int64_t B, int64_t n, int N, int H
     if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
     if (!wave_h || !feat_h) return fail(GSS_EINVAL, "stft_host: null pointer");
     if (B <= 0) return B == 0 ? GSS_OK : fail(GSS_EINVAL, "stft_host: B < 0");
-    std::lock_guard<std::mutex> lk(g_ws_mu);
+    HostWs* ws = nullptr;
+    if (int rc = host_ws(&ws)) return rc;
+    std::lock_guard<std::mutex> lk(ws->mu);
+    if (!ws->st) CK(cudaStreamCreateWithFlags(&ws->st, cudaStreamNonBlocking));
     const size_t bi = sizeof(float) * B * n, bo = sizeof(float) * B * T * N;
-    if (int rc = g_ws_in.reserve(bi)) return rc;
-    if (int rc = g_ws_out.reserve(bo)) return rc;
-    CK(cudaMemcpyAsync(g_ws_in.p, wave_h, bi, cudaMemcpyHostToDevice, 0));
-    if (int rc = gss_stft_packed((const float*)g_ws_in.p, B, n, n, N, H, flags, eps, (float*)g_ws_out.p, nullptr)) return rc;
-    CK(cudaMemcpyAsync(feat_h, g_ws_out.p, bo, cudaMemcpyDeviceToHost, 0));
-    CK(cudaStreamSynchronize(0));
+    if (int rc = ws->in.reserve(bi)) return rc;
+    if (int rc = ws->out.reserve(bo)) return rc;
+    CK(cudaMemcpyAsync(ws->in.p, wave_h, bi, cudaMemcpyHostToDevice, ws->st));
+    if (int rc = gss_stft_packed((const float*)ws->in.p, B, n, n, N, H, flags, eps, (float*)ws->out.p, ws->st)) return rc;
+    CK(cudaMemcpyAsync(feat_h, ws->out.p, bo, cudaMemcpyDeviceToHost, ws->st));
+    CK(cudaStreamSynchronize(ws->st));
     return GSS_OK;
 }
 
@@ -1000,15 +1058,18 @@ int gss_istft_packed_host(const float* feat_h, int64_t R, int64_t T, int N, int 
     if (!feat_h || !wave_h) return fail(GSS_EINVAL, "istft_host: null pointer");
     if (R <= 0) return R == 0 ? GSS_OK : fail(GSS_EINVAL, "istft_host: R < 0");
     if (T < 2 || H < 1) return fail(GSS_EINVAL, "istft_host: bad shape");
-    std::lock_guard<std::mutex> lk(g_ws_mu);
+    HostWs* ws = nullptr;
+    if (int rc = host_ws(&ws)) return rc;
+    std::lock_guard<std::mutex> lk(ws->mu);
+    if (!ws->st) CK(cudaStreamCreateWithFlags(&ws->st, cudaStreamNonBlocking));
     const int64_t len = (T - 1) * H;
     const size_t bi = sizeof(float) * R * T * N, bo = sizeof(float) * R * len;
-    if (int rc = g_ws_in.reserve(bi)) return rc;
-    if (int rc = g_ws_out.reserve(bo)) return rc;
-    CK(cudaMemcpyAsync(g_ws_in.p, feat_h, bi, cudaMemcpyHostToDevice, 0));
-    if (int rc = gss_istft_packed((const float*)g_ws_in.p, R, T, N, H, flags, eps, (float*)g_ws_out.p, len, nullptr)) return rc;
-    CK(cudaMemcpyAsync(wave_h, g_ws_out.p, bo, cudaMemcpyDeviceToHost, 0));
-    CK(cudaStreamSynchronize(0));
+    if (int rc = ws->in.reserve(bi)) return rc;
+    if (int rc = ws->out.reserve(bo)) return rc;
+    CK(cudaMemcpyAsync(ws->in.p, feat_h, bi, cudaMemcpyHostToDevice, ws->st));
+    if (int rc = gss_istft_packed((const float*)ws->in.p, R, T, N, H, flags, eps, (float*)ws->out.p, len, ws->st)) return rc;
+    CK(cudaMemcpyAsync(wave_h, ws->out.p, bo, cudaMemcpyDeviceToHost, ws->st));
+    CK(cudaStreamSynchronize(ws->st));
     return GSS_OK;
 }
 
@@ -1021,19 +1082,20 @@ int gss_stft_h2d_async(const float* wave_h, float* wave_d, int64_t B, int64_t n,
     if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
     if (!wave_h || !wave_d || !feat_d) return fail(GSS_EINVAL, "stft_h2d: null pointer");
     if (chunks < 1 || ld < n) return fail(GSS_EINVAL, "stft_h2d: bad chunks/ld");
-    if (int rc = g_cs.init()) return rc;
+    GSS_CS_LOCKED(cs);
     cudaStream_t st = (cudaStream_t)stream;
     // the upload may overwrite a wave_d that kernels already enqueued on `stream` still read
-    CK(cudaEventRecord(g_cs.order, st));
-    CK(cudaStreamWaitEvent(g_cs.h2d, g_cs.order, 0));
+    CK(cudaEventRecord(cs.order, st));
+    CK(cudaStreamWaitEvent(cs.h2d, cs.order, 0));
     const int64_t per = (B + chunks - 1) / chunks;
     int k = 0;
     for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
         const int64_t nb = (B - b0 < per) ? B - b0 : per;
-        CK(cudaMemcpy2DAsync(wave_d + b0 * ld, sizeof(float) * ld, wave_h + b0 * n, sizeof(float) * n, sizeof(float) * n, nb,
-                             cudaMemcpyHostToDevice, g_cs.h2d));
-        cudaEvent_t ev = g_cs.ev[k % 8];
-        CK(cudaEventRecord(ev, g_cs.h2d));
+        if (ld == n) CK(cudaMemcpyAsync(wave_d + b0 * ld, wave_h + b0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, cs.h2d));   // pitch == width: one linear copy
+        else CK(cudaMemcpy2DAsync(wave_d + b0 * ld, sizeof(float) * ld, wave_h + b0 * n, sizeof(float) * n, sizeof(float) * n, nb,
+                                  cudaMemcpyHostToDevice, cs.h2d));
+        cudaEvent_t ev = cs.ev[k % 8];
+        CK(cudaEventRecord(ev, cs.h2d));
         CK(cudaStreamWaitEvent(st, ev, 0));
         if (int rc = gss_stft_packed(wave_d + b0 * ld, nb, n, ld, N, H, flags, eps, feat_d + b0 * T * N, stream)) return rc;
     }
@@ -1053,10 +1115,10 @@ int gss_mask_istft_d2h_async(const float* wave_d, const float* mask_d, int64_t B
     if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
     if (!out_h || !out_d) return fail(GSS_EINVAL, "mask_istft_d2h: null pointer");
     if (chunks < 1) return fail(GSS_EINVAL, "mask_istft_d2h: bad chunks");
-    if (int rc = g_cs.init()) return rc;
+    GSS_CS_LOCKED(cs);
     cudaStream_t st = (cudaStream_t)stream;
     // a download that still reads this out_d (an earlier batch through the same workspace) goes first
-    if (CopyStreams::Tag* t = CopyStreams::find(g_cs.src, out_d)) CK(cudaStreamWaitEvent(st, t->ev, 0));
+    if (CopyStreams::Tag* t = CopyStreams::find(cs.src, out_d)) CK(cudaStreamWaitEvent(st, t->ev, 0));
     const int64_t len = (T - 1) * H;
     const int64_t per = (B + chunks - 1) / chunks;
     int k = 0;
@@ -1064,17 +1126,18 @@ int gss_mask_istft_d2h_async(const float* wave_d, const float* mask_d, int64_t B
         const int64_t nb = (B - b0 < per) ? B - b0 : per;
         if (int rc = gss_mask_istft(wave_d + b0 * ld, mask_d + b0 * S * T * (N / 2), nb, S, n, ld, N, H,
                                     out_d + b0 * S * ld_out, ld_out, stream)) return rc;
-        cudaEvent_t ev = g_cs.ev[k % 8];
+        cudaEvent_t ev = cs.ev[k % 8];
         CK(cudaEventRecord(ev, st));
-        CK(cudaStreamWaitEvent(g_cs.d2h, ev, 0));
-        CK(cudaMemcpy2DAsync(out_h + b0 * S * len, sizeof(float) * len, out_d + b0 * S * ld_out, sizeof(float) * ld_out,
-                             sizeof(float) * len, nb * S, cudaMemcpyDeviceToHost, g_cs.d2h));
+        CK(cudaStreamWaitEvent(cs.d2h, ev, 0));
+        if (ld_out == len) CK(cudaMemcpyAsync(out_h + b0 * S * len, out_d + b0 * S * ld_out, sizeof(float) * len * nb * S, cudaMemcpyDeviceToHost, cs.d2h));
+        else CK(cudaMemcpy2DAsync(out_h + b0 * S * len, sizeof(float) * len, out_d + b0 * S * ld_out, sizeof(float) * ld_out,
+                                  sizeof(float) * len, nb * S, cudaMemcpyDeviceToHost, cs.d2h));
     }
     CopyStreams::Tag* ts = nullptr; CopyStreams::Tag* td = nullptr;
-    if (int rc = g_cs.claim(g_cs.src, out_d, &ts)) return rc;
-    if (int rc = g_cs.claim(g_cs.dst, out_h, &td)) return rc;
-    CK(cudaEventRecord(ts->ev, g_cs.d2h));
-    CK(cudaEventRecord(td->ev, g_cs.d2h));
+    if (int rc = cs.claim(cs.src, out_d, &ts)) return rc;
+    if (int rc = cs.claim(cs.dst, out_h, &td)) return rc;
+    CK(cudaEventRecord(ts->ev, cs.d2h));
+    CK(cudaEventRecord(td->ev, cs.d2h));
     return GSS_OK;
 }
 
@@ -1088,18 +1151,19 @@ int gss_stft_h2d_i16_async(const int16_t* pcm_h, int16_t* pcm_d, float* wave_d, 
     if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
     if (!pcm_h || !pcm_d || !wave_d || !feat_d) return fail(GSS_EINVAL, "stft_h2d_i16: null pointer");
     if (chunks < 1 || ld < n) return fail(GSS_EINVAL, "stft_h2d_i16: bad chunks/ld");
-    if (int rc = g_cs.init()) return rc;
+    GSS_CS_LOCKED(cs);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaEventRecord(g_cs.order, st));
-    CK(cudaStreamWaitEvent(g_cs.h2d, g_cs.order, 0));
+    CK(cudaEventRecord(cs.order, st));
+    CK(cudaStreamWaitEvent(cs.h2d, cs.order, 0));
     const int64_t per = (B + chunks - 1) / chunks;
     int k = 0;
     for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
         const int64_t nb = (B - b0 < per) ? B - b0 : per;
-        CK(cudaMemcpy2DAsync(pcm_d + b0 * ld, sizeof(int16_t) * ld, pcm_h + b0 * n, sizeof(int16_t) * n, sizeof(int16_t) * n, nb,
-                             cudaMemcpyHostToDevice, g_cs.h2d));
-        cudaEvent_t ev = g_cs.ev[k % 8];
-        CK(cudaEventRecord(ev, g_cs.h2d));
+        if (ld == n) CK(cudaMemcpyAsync(pcm_d + b0 * ld, pcm_h + b0 * n, sizeof(int16_t) * n * nb, cudaMemcpyHostToDevice, cs.h2d));
+        else CK(cudaMemcpy2DAsync(pcm_d + b0 * ld, sizeof(int16_t) * ld, pcm_h + b0 * n, sizeof(int16_t) * n, sizeof(int16_t) * n, nb,
+                                  cudaMemcpyHostToDevice, cs.h2d));
+        cudaEvent_t ev = cs.ev[k % 8];
+        CK(cudaEventRecord(ev, cs.h2d));
         CK(cudaStreamWaitEvent(st, ev, 0));
         if (int rc = gss_stft_packed_i16(pcm_d + b0 * ld, nb, n, ld, N, H, flags, eps, feat_d + b0 * T * N, stream)) return rc;
         gss::i16_to_f32_kernel<<<grid_for(nb * ld, 256), 256, 0, st>>>(pcm_d + b0 * ld, wave_d + b0 * ld, nb * ld);
@@ -1115,10 +1179,10 @@ int gss_mask_istft_d2h_pcm16_async(const float* wave_d, const float* mask_d, int
     if (int rc = frame_count(n, N, H, &T, nullptr)) return rc;
     if (!out_d || !minmax_d || !pcm_d || !pcm_h) return fail(GSS_EINVAL, "mask_istft_d2h_pcm16: null pointer");
     if (chunks < 1) return fail(GSS_EINVAL, "mask_istft_d2h_pcm16: bad chunks");
-    if (int rc = g_cs.init()) return rc;
+    GSS_CS_LOCKED(cs);
     cudaStream_t st = (cudaStream_t)stream;
     // a download that still reads this pcm_d (an earlier batch through the same workspace) goes first
-    if (CopyStreams::Tag* t = CopyStreams::find(g_cs.src, pcm_d)) CK(cudaStreamWaitEvent(st, t->ev, 0));
+    if (CopyStreams::Tag* t = CopyStreams::find(cs.src, pcm_d)) CK(cudaStreamWaitEvent(st, t->ev, 0));
     const int64_t len = (T - 1) * H;
     const int64_t per = (B + chunks - 1) / chunks;
     int k = 0;
@@ -1128,23 +1192,39 @@ int gss_mask_istft_d2h_pcm16_async(const float* wave_d, const float* mask_d, int
                                     out_d + b0 * S * ld_out, ld_out, stream)) return rc;
         if (int rc = gss_wav16_normalise(out_d + b0 * S * ld_out, nb * S, len, ld_out, minmax_d + 2 * b0 * S,
                                          pcm_d + b0 * S * len, stream)) return rc;
-        cudaEvent_t ev = g_cs.ev[k % 8];
+        cudaEvent_t ev = cs.ev[k % 8];
         CK(cudaEventRecord(ev, st));
-        CK(cudaStreamWaitEvent(g_cs.d2h, ev, 0));
-        CK(cudaMemcpyAsync(pcm_h + b0 * S * len, pcm_d + b0 * S * len, sizeof(int16_t) * nb * S * len, cudaMemcpyDeviceToHost, g_cs.d2h));
+        CK(cudaStreamWaitEvent(cs.d2h, ev, 0));
+        CK(cudaMemcpyAsync(pcm_h + b0 * S * len, pcm_d + b0 * S * len, sizeof(int16_t) * nb * S * len, cudaMemcpyDeviceToHost, cs.d2h));
     }
     CopyStreams::Tag* ts = nullptr; CopyStreams::Tag* td = nullptr;
-    if (int rc = g_cs.claim(g_cs.src, pcm_d, &ts)) return rc;
-    if (int rc = g_cs.claim(g_cs.dst, pcm_h, &td)) return rc;
-    CK(cudaEventRecord(ts->ev, g_cs.d2h));
-    CK(cudaEventRecord(td->ev, g_cs.d2h));
+    if (int rc = cs.claim(cs.src, pcm_d, &ts)) return rc;
+    if (int rc = cs.claim(cs.dst, pcm_h, &td)) return rc;
+    CK(cudaEventRecord(ts->ev, cs.d2h));
+    CK(cudaEventRecord(td->ev, cs.d2h));
     return GSS_OK;
 }
 
 int gss_wait_host(const void* host_ptr) {
-    if (!g_cs.ok) return GSS_OK;
-    if (!host_ptr) { CK(cudaStreamSynchronize(g_cs.d2h)); return GSS_OK; }     // every pending download
-    if (CopyStreams::Tag* t = CopyStreams::find(g_cs.dst, host_ptr)) CK(cudaEventSynchronize(t->ev));
+    // any thread may wait: the tags are looked up under the owning device's mutex, the wait itself happens outside it
+    if (host_ptr) {
+        for (CopyStreams& c : g_cs_dev) {
+            cudaEvent_t ev = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(c.mu);
+                if (!c.ok) continue;
+                if (CopyStreams::Tag* t = CopyStreams::find(c.dst, host_ptr)) ev = t->ev;
+            }
+            if (ev) { CK(cudaEventSynchronize(ev)); return GSS_OK; }
+        }
+    }
+    // NULL, or a pointer without a tag (never enqueued, or its tag was recycled after a drain): every pending
+    // download of the current device - never a silent return before the data has landed
+    CopyStreams* cp = nullptr;
+    if (int rc = copy_streams(&cp)) return rc;
+    cudaStream_t d2h = nullptr;
+    { std::lock_guard<std::mutex> lk(cp->mu); if (cp->ok) d2h = cp->d2h; }
+    if (d2h) CK(cudaStreamSynchronize(d2h));
     return GSS_OK;
 }
 

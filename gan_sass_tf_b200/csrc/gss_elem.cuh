@@ -379,6 +379,19 @@ __global__ void __launch_bounds__(256) apply_mask_bwd_kernel(const float* __rest
     }
 }
 
+// Batch assembly of the device-resident corpus (app/datasets/wave.py; padding rule of app/datasets/timit.py:47-52): row r of
+// out [B, ld] = utterance idx[r] of the flat int16 store (offsets[i] .. offsets[i] + lengths[i]), zero-padded to ld.
+__global__ void __launch_bounds__(256) gather_rows_i16_kernel(const int16_t* __restrict__ flat, const int64_t* __restrict__ offsets,
+                                                              const int64_t* __restrict__ lengths, const int64_t* __restrict__ idx,
+                                                              int64_t B, int64_t ld, int16_t* __restrict__ out) {
+    const int64_t total = B * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ld, c = i - r * ld;
+        const int64_t u = __ldg(idx + r);
+        out[i] = c < __ldg(lengths + u) ? __ldg(flat + __ldg(offsets + u) + c) : (int16_t)0;
+    }
+}
+
 // int16 PCM -> float32 (same values, no rescale: the reference feeds raw sample values to SciPy, process.py:97)
 __global__ void __launch_bounds__(256) i16_to_f32_kernel(const int16_t* __restrict__ in, float* __restrict__ out, int64_t total) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)

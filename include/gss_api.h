@@ -49,6 +49,10 @@ const char* gss_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t     gss_launch_count(void);
 
+#ifdef GSS_EXPERIMENTAL
+/* Only in lib/libgss_experimental.so (built with -DGSS_EXPERIMENTAL; what the cross-check tests and the tuning tools
+ * load).  The product library exports neither: it keeps no process-wide mutable switches. */
+
 /* Kernel selection: 0 = automatic (register-exchange streaming kernels for N = 256 / 512, shared-memory team
  * kernels for 1024 / 2048 / 4096, per-frame kernels for 64 / 128), 1 = no register-exchange kernels (team kernels
  * take 256 / 512 too), 2 = per-frame kernels only.  Process-wide; meant for cross-checking the implementations
@@ -61,6 +65,7 @@ int         gss_set_path(int path);
  * measured design alternatives and cross-checks.  Process-wide; the environment variable GSS_SYNTH_SPLIT
  * sets the initial value. */
 int         gss_set_synth_variant(int variant);
+#endif /* GSS_EXPERIMENTAL */
 
 /* FFT sizes this build has kernels for (writes up to `cap` entries, returns the count);
  * hops N/2 (the reference's SciPy default), N/4 and N/8 are supported for each. */
@@ -126,6 +131,12 @@ int gss_mask_istft_feature_ae(const float* feat, const float* mask, int64_t B, i
  * so the all-reduce can follow on the same stream without a host round trip. */
 int gss_metric_finalise(const float* ae_rows, const float* snr, int64_t B, int m, int n, double elems_per_row,
                         float* vec4, void* stream);
+
+/* Batch assembly for the device-resident corpus that replaces the FFT_SIZE-baked pickles (TIMIT/process.py:80-161,
+ * app/datasets/timit.py:47-52): out[r, :] = utterance idx[r] of the flat int16 store, zero-padded to ld samples.
+ * offsets / lengths [n_utterances] and idx [B] are int64 device arrays.  One launch per batch. */
+int gss_gather_rows_i16(const int16_t* flat, const int64_t* offsets, const int64_t* lengths, const int64_t* idx,
+                        int64_t B, int64_t ld, int16_t* out, void* stream);
 
 /* A7 alone on packed features: mix [B,T,N], mask [B,S,T,N/2] -> out [B*S,T,N] */
 int gss_apply_mask(const float* mix, const float* mask, int64_t B, int S, int64_t T, int N,

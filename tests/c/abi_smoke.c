@@ -22,7 +22,8 @@ int main(void) {
     CHECK(gss_stft_packed(NULL, 1, 4000, 4000, 512, 128, 0, 1e-7f, NULL, NULL) == GSS_EINVAL);
     CHECK(gss_mask_istft(NULL, NULL, 1, 3, 4000, 4000, 512, 128, NULL, 4096, NULL) == GSS_EINVAL);
     CHECK(gss_mix_features(NULL, NULL, 1, 3, 10, 256, 0, 1e-7f, NULL, NULL, NULL) == GSS_EINVAL);
-    CHECK(gss_set_path(7) == GSS_EINVAL && gss_set_path(0) == GSS_OK);
+    CHECK(gss_mask_istft_feature(NULL, NULL, 1, 3, 10, 512, 128, 0, NULL, 4096, NULL) == GSS_EINVAL);
+    CHECK(gss_metric_finalise(NULL, NULL, 1, 1, 1, 1.0, NULL, NULL) == GSS_EINVAL);
     printf("abi_smoke ok (libgss %d)\n", gss_version());
     return 0;
 }

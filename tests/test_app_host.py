@@ -49,8 +49,10 @@ def test_driver_mode_switch_without_gpu():
     from gan_sass_tf_b200 import main as drv
     with pytest.raises(ValueError, match='Unknown mode'):
         drv.main(['-m', 'bogus'])
-    with pytest.raises(NotImplementedError):
-        drv.main(['-m', 'train'])
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match='CUDA only'):       # the mode is wired (tests/test_gpu_app.py trains); no CPU fallback
+            drv.main(['-m', 'train', '-ne', '1'])
     with pytest.raises(FileNotFoundError):
         drv.load_wavfile(None)
 

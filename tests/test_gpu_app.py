@@ -350,3 +350,78 @@ def test_demo_mode_writes_separated_files(T, ops, hp, tmp_path):
         assert pcm.min() == 0 and pcm.max() >= 32766
     res = drv.g_model.test(drv.g_dataset)
     assert set(res) == {'SNR', 'AE'} and np.isfinite(res['SNR']) and np.isfinite(res['AE'])
+
+
+# ---- -m train: the spectral slice of main.py:568-624 through the native ops ---------------------------------
+@pytest.mark.parametrize("sep_type", ["toy", "toy-mask"])
+def test_train_mode_runs_and_loss_falls(T, ops, hp, tmp_path, monkeypatch, sep_type):
+    from gan_sass_tf_b200 import main as drv
+    monkeypatch.chdir(tmp_path)                                   # saves/<name>_e<k> land in the temporary directory
+    hp.FFT_SIZE, hp.HOP_SIZE, hp.BATCH_SIZE, hp.MAX_N_SIGNAL = 256, None, 4, 2
+    hp.SEPARATOR_TYPE, hp.DATASET_TYPE = sep_type, 'toy'
+    drv.main(['-m', 'train', '-ne', '1', '-n', 'unit', '-o', os.path.join(tmp_path, 'final.pt')])
+    assert os.path.exists(os.path.join(tmp_path, 'saves', 'unit_e1')) and os.path.exists(os.path.join(tmp_path, 'final.pt'))
+    model = drv.g_model
+    ds = drv.g_dataset
+    reports = model.train(ds, 3, lr=2e-3, save_on_epoch=False, test_on_epoch=True, out=open(os.devnull, 'w'))
+    assert len(reports) == 3 and all(np.isfinite(r['AE']) and np.isfinite(r['test_SNR']) for r in reports)
+    assert reports[-1]['AE'] < reports[0]['AE']                   # Adam on the auto-encoder loss makes progress
+    # a checkpoint restores the weights bit for bit
+    before = [p.detach().clone() for p in model.parameters()]
+    model.save_params(os.path.join(tmp_path, 'ck.pt'))
+    for p in model.parameters():
+        p.data.add_(1.0)
+    model.load_params(os.path.join(tmp_path, 'ck.pt'))
+    assert all(T.equal(a, b) for a, b in zip(before, model.parameters()))
+
+
+def test_load_wavfile_stereo_and_short(T, ops, hp, tmp_path):
+    """a (nsamples, nchannels) WAV: the FIRST CHANNEL is used (upstream's indexing takes the first frame, SURVEY appendix B);
+    a clip shorter than FFT_SIZE is rejected with a message that names the file."""
+    import scipy.io.wavfile
+    from gan_sass_tf_b200 import main as drv
+    hp.FFT_SIZE, hp.HOP_SIZE = 256, None
+    rng = np.random.default_rng(11)
+    st = (rng.standard_normal((4000, 2)) * 3000).astype(np.int16)
+    path = os.path.join(tmp_path, "stereo.wav")
+    scipy.io.wavfile.write(path, 16000, st)
+    feat = drv.load_wavfile(path)
+    ref = R.load_wave_features(st[:, 0].copy(), 16000, 256)
+    assert tuple(feat.shape) == ref.shape and R.rel_l2(feat.cpu().numpy(), ref) < REL_L2
+    short = os.path.join(tmp_path, "short.wav")
+    scipy.io.wavfile.write(short, 16000, st[:100, 0].copy())
+    with pytest.raises(ValueError, match="fewer than FFT_SIZE"):
+        drv.load_wavfile(short)
+
+
+def test_waveform_dataset_from_directory(T, ops, hp, tmp_path):
+    """file-backed corpus (TIMIT/process.py:89-110): 16 kHz WAVs under a directory, 'sa*' skipped, other rates rejected;
+    the gathered batch equals the oracle's features of the zero-padded utterances; epochs shuffle differently."""
+    import scipy.io.wavfile
+    from gan_sass_tf_b200.app.datasets.wave import WaveformData
+    hp.FFT_SIZE, hp.HOP_SIZE = 256, None
+    rng = np.random.default_rng(5)
+    lens = {"a1.wav": 3001, "b2.wav": 5000, "sa1.wav": 4000, "c3.wav": 2500, "d4.wav": 2600}
+    os.makedirs(os.path.join(tmp_path, "dr1"))
+    waves = {}
+    for name, n in lens.items():
+        waves[name] = (rng.standard_normal(n) * 2500).astype(np.int16)
+        scipy.io.wavfile.write(os.path.join(tmp_path, "dr1", name), 16000, waves[name])
+    ds = WaveformData()
+    assert ds.add_directory('train', str(tmp_path)) == 4                          # sa1.wav skipped
+    feats, frames = next(iter(ds.epoch('train', 4)))
+    order = sorted((n for n in lens if not n.startswith("sa")), key=lambda k: lens[k])
+    n_max = feats.shape[1]
+    for r, name in enumerate(order):
+        x = np.zeros(5000, np.int16)
+        x[:lens[name]] = waves[name]
+        ref = R.stft_feature_np(x, 256, 128)
+        assert feats.shape[1] == ref.shape[0] and R.rel_l2(feats[r].cpu().numpy(), ref) < REL_L2
+        assert int(frames[r]) == R.frame_count(lens[name], 256, 128)[0]
+    o1 = [f.shape for f, _ in ds.epoch('train', 1, shuffle=True)]
+    o2 = [f.shape for f, _ in ds.epoch('train', 1, shuffle=True)]
+    o3 = [f.shape for f, _ in ds.epoch('train', 1, shuffle=True)]
+    assert sorted(o1) == sorted(o2) and (o1 != o2 or o1 != o3)                    # same batches, a new order per epoch
+    scipy.io.wavfile.write(os.path.join(tmp_path, "dr1", "e5.wav"), 8000, waves["a1.wav"])
+    with pytest.raises(ValueError, match="Sampling rate"):
+        WaveformData().add_directory('train', str(tmp_path))

@@ -31,6 +31,20 @@ def ops():
     return o
 
 
+@pytest.fixture()
+def experimental():
+    """lib/libgss_experimental.so for the duration of a test: the product library has neither the kernel-family switches
+    nor the kernels they select (role-split / tensor-memory synthesis, team kernels at 256 / 512)."""
+    from gan_sass_tf_b200 import _native
+    _native.load_experimental()
+    try:
+        yield _native
+    finally:
+        _native.set_path(0)
+        _native.set_synth_variant(0)
+        _native.unload_experimental()
+
+
 def dev(T, a):
     return T.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -227,7 +241,7 @@ def test_apply_mask_matches_oracle(T, ops):
     assert np.array_equal(out, R.apply_mask(mix, mask))       # one multiply per element: bit-exact
 
 
-def test_streaming_and_generic_paths_agree(T, ops):
+def test_streaming_and_generic_paths_agree(T, ops, experimental):
     """N = 512 has three independent implementations (register-exchange streaming FFT, shared-memory
     Stockham team FFT, the per-frame fallback): same inputs, results within float32 rounding."""
     from gan_sass_tf_b200 import _native
@@ -250,7 +264,7 @@ def test_streaming_and_generic_paths_agree(T, ops):
 
 
 @pytest.mark.parametrize("H", [64, 128, 256])
-def test_synthesis_variants_agree(T, ops, H):
+def test_synthesis_variants_agree(T, ops, H, experimental):
     """The three N = 512 fused-synthesis kernels (register-resident, role-split CTAs, per-thread state parked in
     tensor memory) against the oracle and against each other: ragged and odd lengths, several chunks per row."""
     from gan_sass_tf_b200 import _native
@@ -277,7 +291,7 @@ def test_synthesis_variants_agree(T, ops, H):
 
 @pytest.mark.parametrize("N,H", [(256, 32), (256, 64), (256, 128), (1024, 128), (1024, 256), (1024, 512),
                                  (2048, 256), (2048, 512), (2048, 1024), (4096, 512), (4096, 1024), (4096, 2048)])
-def test_team_kernels_all_sizes(T, ops, N, H):
+def test_team_kernels_all_sizes(T, ops, N, H, experimental):
     """every (N, hop) the shared-memory team kernels cover: all three ops against the oracle, ragged length,
     several chunks per row (long rows), S = 1..4, and the per-frame fallback as a second opinion."""
     from gan_sass_tf_b200 import _native
@@ -517,3 +531,51 @@ def test_cuda_graph_capture_and_replay(T, ops):
         T.cuda.synchronize()
         assert R.rel_l2(feat.cpu().numpy(), R.to_log_signal(R.stft_feature_np(xs, N, H))) < REL_L2
         assert R.rel_l2(out.cpu().numpy(), R.mask_istft_np(xs, ms, N, H).reshape(B * S, -1)) < REL_L2
+
+
+# --------------------------------------------------------------------------
+# BASELINE configs C4 and C5 at full size: properties + sub-batches against the oracle
+# --------------------------------------------------------------------------
+def _full_size_case(T, ops, N, H, n, B, S, rows, seed):
+    """STFT -> masks that sum to one -> both synthesis kernels at full size: shapes, >= 100 dB reconstruction over the WHOLE
+    batch (a size-independent property), the rows in `rows` against the float64 oracle, both paths against each other."""
+    g = T.Generator(device="cuda").manual_seed(seed)
+    x = T.randn(B, n, device="cuda", generator=g) * 0.1
+    Tn, nadd = R.frame_count(n, N, H)
+    lin, lg = ops.stft_dual(x, N, H)
+    assert lin.shape == (B, Tn, N) and lg.shape == (B, Tn, N)
+    m = T.rand(B, S, Tn, N // 2, device="cuda", generator=g) + 0.05
+    m /= m.sum(dim=1, keepdim=True)
+    y = ops.mask_istft_feature(lin, m, H)
+    assert y.shape == (B * S, (Tn - 1) * H) and (Tn - 1) * H == n + nadd
+    for b0 in range(0, B, 512):                                        # reconstruction, accumulated in float64 by blocks
+        sl = slice(b0, min(b0 + 512, B))
+        rec = y.reshape(B, S, -1)[sl].sum(dim=1)[:, :n]
+        err = (rec - x[sl]).double().pow(2).sum() / x[sl].double().pow(2).sum()
+        assert 10 * np.log10(1.0 / float(err)) >= 100.0
+    for r in rows:
+        xr = x[r:r + 1].cpu().numpy()
+        ref = R.mask_istft_np(xr, m[r:r + 1].cpu().numpy(), N, H).reshape(S, -1)
+        assert R.rel_l2(y.reshape(B, S, -1)[r].cpu().numpy(), ref) < REL_L2
+        assert R.rel_l2(lin[r].cpu().numpy(), R.stft_feature_np(xr[0], N, H, np.float64, np.float64)) < REL_L2
+        assert R.rel_l2(lg[r].cpu().numpy(), R.to_log_signal(R.stft_feature_np(xr[0], N, H, np.float64, np.float64))) < REL_L2
+    del lin, lg
+    y2 = ops.mask_istft(x, m, N, H)                                     # the waveform-fed kernel on the same inputs
+    d = (y2 - y).double().pow(2).sum() / y.double().pow(2).sum()
+    assert float(d) ** 0.5 < 3e-6
+
+
+def test_c4_share_full_size(T, ops):
+    """C4 per-GPU share at 8 GPUs: 1024 x 4 s, N = 512, H = 128, S = 3."""
+    _full_size_case(T, ops, 512, 128, 64000, 1024, 3, rows=(0, 511, 1023), seed=41)
+
+
+def test_c4_full_size_one_gpu(T, ops):
+    """C4 whole: 8192 x 4 s on one GPU (B*T*N = 2.1e9 elements: every index product crosses 2^31); rows 0, 4095, 8191."""
+    _full_size_case(T, ops, 512, 128, 64000, 8192, 3, rows=(0, 4095, 8191), seed=42)
+
+
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048, 4096])
+def test_c5_sweep_full_size(T, ops, N):
+    """C5: B = 1024 x 3 s, hop N/4, every FFT size of the sweep."""
+    _full_size_case(T, ops, N, N // 4, 48000, 1024, 3, rows=(0, 1023), seed=50 + N)

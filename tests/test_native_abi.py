@@ -17,9 +17,12 @@ def native():
     return _native
 
 
-def _declared_symbols():
+def _declared_symbols(experimental=False):
+    """symbols include/gss_api.h declares; the GSS_EXPERIMENTAL block counts only for the experimental flavour"""
     src = open(os.path.join(ROOT, "include", "gss_api.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    if not experimental:
+        src = re.sub(r"#ifdef GSS_EXPERIMENTAL.*?#endif", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(gss_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -31,6 +34,15 @@ def test_header_symbols_exported(native):
         assert hasattr(h, s), f"{s} declared in include/gss_api.h but not exported by libgss.so"
     # and the ctypes table binds exactly the declared surface
     assert sorted(native.SIGNATURES) == syms
+    # the product library keeps no process-wide switches: they live in the experimental flavour only
+    xs = _declared_symbols(experimental=True)
+    extra = sorted(set(xs) - set(syms))
+    assert extra == sorted(native.EXPERIMENTAL_SIGNATURES) == ["gss_set_path", "gss_set_synth_variant"]
+    for s in extra:
+        assert not hasattr(h, s), f"{s} must not be exported by the product library"
+    hx = ctypes.CDLL(native.EXPERIMENTAL_LIB_PATH)
+    for s in xs:
+        assert hasattr(hx, s), f"{s} missing from libgss_experimental.so"
 
 
 def test_version_and_sizes(native):

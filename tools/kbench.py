@@ -7,7 +7,9 @@ from gan_sass_tf_b200.app import ops
 from gan_sass_tf_b200 import _native
 
 N, H, B, n = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 and sys.argv[1].isdigit() else (512, 128, 256, 48000)
-_native.set_path(int(os.environ.get("GSS_PATH", "0")))      # 1: no register-exchange kernels, 2: per-frame fallback only
+if os.environ.get("GSS_PATH"):                              # 1: no register-exchange kernels, 2: per-frame fallback only
+    _native.load_experimental()                             # the switches exist in lib/libgss_experimental.so only
+    _native.set_path(int(os.environ["GSS_PATH"]))
 T, _ = _native.frame_count(n, N, H)
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
