@@ -636,8 +636,12 @@ template <int N> constexpr size_t synth_feat_bytes() {
     return sizeof(float2) * 2 * (size_t)(N + N / Plan<N>::R0) + sizeof(float) * 4 * (size_t)N + 2 * sizeof(uint64_t);
 }
 
+// resident CTAs per SM the feature-fed kernel is compiled for (tuning macro; default = the waveform-fed kernel's)
+#ifndef GSS_TEAM_FEAT_MINB
+#define GSS_TEAM_FEAT_MINB(N) Plan<N>::MINB_SYNTH
+#endif
 template <int N, int HS, int ST>
-__global__ void __launch_bounds__(TGeo<N, HS>::TPT, Plan<N>::MINB_SYNTH) mask_istft_feat_kernel(const SynthFeatArgs p) {
+__global__ void __launch_bounds__(TGeo<N, HS>::TPT, GSS_TEAM_FEAT_MINB(N)) mask_istft_feat_kernel(const SynthFeatArgs p) {
     typedef TGeo<N, HS> G;
     constexpr int NH = N / 2, R0 = G::R0;
     extern __shared__ float4 smem4[];

@@ -139,7 +139,7 @@ class Model(object):
                 opt.zero_grad(set_to_none=True)
                 loss.backward()
                 opt.step()
-                rep['AE'] += float(loss); rep['SNR'] += float(snr); nb += 1
+                rep['AE'] += float(loss.detach()); rep['SNR'] += float(snr); nb += 1
                 out.write(':'); out.flush()
             rep = {k: v / max(nb, 1) for k, v in rep.items()}
             out.write('\n')

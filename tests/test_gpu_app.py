@@ -365,7 +365,12 @@ def test_train_mode_runs_and_loss_falls(T, ops, hp, tmp_path, monkeypatch, sep_t
     ds = drv.g_dataset
     reports = model.train(ds, 3, lr=2e-3, save_on_epoch=False, test_on_epoch=True, out=open(os.devnull, 'w'))
     assert len(reports) == 3 and all(np.isfinite(r['AE']) and np.isfinite(r['test_SNR']) for r in reports)
-    assert reports[-1]['AE'] < reports[0]['AE']                   # Adam on the auto-encoder loss makes progress
+    if sep_type == 'toy':
+        assert reports[-1]['AE'] < reports[0]['AE']               # Adam on the auto-encoder loss makes progress
+    else:
+        # softmax masks sum to one, so sum_s mask_s * mix - mix = 0: the auto-encoder term vanishes identically (the
+        # reference's generator objective is ae - gan, main.py:481; its GAN term is out of scope) - a check of A7 + A12
+        assert all(r['AE'] < 1e-12 and r['test_AE'] < 1e-12 for r in reports)
     # a checkpoint restores the weights bit for bit
     before = [p.detach().clone() for p in model.parameters()]
     model.save_params(os.path.join(tmp_path, 'ck.pt'))
