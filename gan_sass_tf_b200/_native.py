@@ -33,6 +33,8 @@ SIGNATURES = {
     "gss_mask_istft_feature": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, c_int, _P, c_int64, _P]),
     "gss_mask_istft_feature_ae": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, c_int, _P, c_int64, _P, _P]),
     "gss_metric_finalise": (c_int, [_P, _P, c_int64, c_int, c_int, ctypes.c_double, _P, _P]),
+    "gss_resample_workspace_bytes": (ctypes.c_size_t, [c_int64, c_int64]),
+    "gss_resample_f64": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P, ctypes.c_size_t, _P]),
     "gss_gather_rows_i16": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P]),
     "gss_apply_mask": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P]),
     "gss_ola_norm_scale": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, _P]),

@@ -549,21 +549,20 @@ def resample_pad_size(length, fft_size=None):
 
 
 def resample(wave, num):
-    """``scipy.signal.resample(x, num)`` (Fourier method, main.py:92) along the last axis of a
-    real CUDA tensor.  One long rFFT / irFFT pair: this edge op calls cuFFT through ``torch.fft``
-    (a library call, not one of the hand-written kernels; SURVEY 8f.3 lists it as "next")."""
-    x = _dev(wave, "resample").to(torch.float64 if wave.dtype == torch.float64 else torch.float32)
+    """``scipy.signal.resample(x, num)`` (Fourier method, main.py:92) along the last axis of a real CUDA tensor:
+    hand-written Bluestein chirp-z transforms over a power-of-two Stockham FFT in float64 (``gss_resample_f64``;
+    SciPy itself promotes the int16 samples to float64).  float32 input is computed in float64 and cast back."""
+    x = _dev(wave, "resample")
+    out_dtype = torch.float64 if wave.dtype == torch.float64 else torch.float32
+    x = x.to(torch.float64).contiguous()
     n, num = x.shape[-1], int(num)
     assert n >= 1 and num >= 1
-    X = torch.fft.rfft(x, dim=-1)
-    m = min(n, num)
-    nyq = m // 2 + 1
-    Y = torch.zeros(x.shape[:-1] + (num // 2 + 1,), dtype=X.dtype, device=x.device)
-    Y[..., :nyq] = X[..., :nyq]
-    if m % 2 == 0:                       # the shared Nyquist bin (scipy.signal.resample, real input)
-        if num < n:
-            Y[..., m // 2] = Y[..., m // 2] * 2.0      # down-sampling: fold the two halves of the bin
-        elif num > n:
-            Y[..., m // 2] = Y[..., m // 2] * 0.5      # up-sampling: split it
-    y = torch.fft.irfft(Y, n=num, dim=-1)
-    return y * (float(num) / float(n))
+    rows = x.numel() // n
+    y = torch.empty(x.shape[:-1] + (num,), dtype=torch.float64, device=x.device)
+    nbytes = int(_n.lib().gss_resample_workspace_bytes(n, num))
+    if nbytes == 0:
+        raise ValueError(f"resample: unsupported lengths n={n}, num={num}")
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _n.check(_n.lib().gss_resample_f64(x.data_ptr(), rows, n, n, num, y.data_ptr(), num, ws.data_ptr(), nbytes, _stream()))
+    return y.to(out_dtype)

@@ -35,6 +35,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
+    # inline variables and the statics of template functions are STB_GNU_UNIQUE by default: the dynamic linker would then
+    # share them between libgss.so and libgss_experimental.so inside one process even under RTLD_LOCAL (e.g. the
+    # "lane tables filled" flags, while each library owns its own __device__ tables)
+    "-Xcompiler", "-fno-gnu-unique",
 ]
 
 

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <cuda_runtime.h>
 
 #include "../../include/gss_api.h"
@@ -38,6 +39,7 @@
 #if GSS_HAS(0)
 #include "gss_elem.cuh"          // non-template kernels: defined in part 0 only
 #include "gss_generic.cuh"
+#include "gss_resample.cuh"
 #endif
 
 namespace gss_shared {
@@ -143,6 +145,12 @@ int frame_count(int64_t n, int N, int H, int64_t* T, int64_t* nadd) {
 // `npairs` pairs; each chunk recomputes `halo` pairs and pays ~2 pairs of set-up.
 // cost = waves over the resident team slots x pairs walked per team.
 gss::ChunkPlan plan_chunks(int64_t rows, int npairs, int halo, int64_t slots) {
+    // the search is O(npairs) (hundreds of thousands of iterations for hour-long rows): remember the last few answers
+    struct Memo { int64_t rows, slots; int npairs, halo; gss::ChunkPlan plan; bool used; };
+    static thread_local Memo memo[8];
+    static thread_local int next = 0;
+    for (const Memo& m : memo)
+        if (m.used && m.rows == rows && m.slots == slots && m.npairs == npairs && m.halo == halo) return m.plan;
     gss::ChunkPlan best{npairs, 1};
     double best_cost = 1e300;
     for (int ppc = 1; ppc <= npairs; ++ppc) {
@@ -152,13 +160,56 @@ gss::ChunkPlan plan_chunks(int64_t rows, int npairs, int halo, int64_t slots) {
         double cost = (double)waves * (ppc + (nchunk > 1 ? halo : 0) + 2.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = gss::ChunkPlan{ppc, nchunk}; }
     }
+    memo[next] = Memo{rows, slots, npairs, halo, best, true};
+    next = (next + 1) % 8;
     return best;
+}
+
+// per (kernel, device), asked from the runtime once: the dynamic shared-memory opt-in and the resident CTAs per SM
+inline std::mutex g_kinfo_mu;
+inline std::unordered_map<uint64_t, int> g_kblocks;      // key -> resident CTAs per SM
+inline std::unordered_map<uint64_t, size_t> g_ksmem;     // key -> dynamic shared memory opted in for
+int kernel_key(const void* kernel, uint64_t* key) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    *key = (uint64_t)(uintptr_t)kernel * 64u + (uint64_t)(dev & 63);
+    return GSS_OK;
+}
+int ensure_smem(const void* kernel, size_t smem) {
+    if (smem <= 48 * 1024) return GSS_OK;
+    uint64_t key = 0;
+    if (int rc = kernel_key(kernel, &key)) return rc;
+    {
+        std::lock_guard<std::mutex> lk(g_kinfo_mu);
+        auto it = g_ksmem.find(key);
+        if (it != g_ksmem.end() && it->second >= smem) return GSS_OK;
+    }
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    std::lock_guard<std::mutex> lk(g_kinfo_mu);
+    g_ksmem[key] = smem;
+    return GSS_OK;
+}
+int kernel_info(const void* kernel, int threads, size_t smem, int* blocks) {
+    uint64_t key = 0;
+    if (int rc = kernel_key(kernel, &key)) return rc;
+    {
+        std::lock_guard<std::mutex> lk(g_kinfo_mu);
+        auto it = g_kblocks.find(key);
+        if (it != g_kblocks.end()) { *blocks = it->second; return GSS_OK; }
+    }
+    if (int rc = ensure_smem(kernel, smem)) return rc;
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) { nb = 1; cudaGetLastError(); }
+    std::lock_guard<std::mutex> lk(g_kinfo_mu);
+    g_kblocks[key] = nb;
+    *blocks = nb;
+    return GSS_OK;
 }
 
 template <typename K>
 int64_t team_slots(K kernel, int warps, int teams, size_t smem) {
     int nb = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, warps * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+    if (kernel_info((const void*)kernel, warps * 32, smem, &nb) != GSS_OK) nb = 1;
     return (int64_t)sm_count() * nb * teams;
 }
 
@@ -189,10 +240,7 @@ int ensure_tables(cudaStream_t st) {
 }
 
 template <typename K>
-int prep(K kernel, size_t smem) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return GSS_OK;
-}
+int prep(K kernel, size_t smem) { return ensure_smem((const void*)kernel, smem); }
 
 #if GSS_HAS(0)
 // ---- any-size path (gss_generic.cuh) -------------------------------------------
@@ -208,10 +256,15 @@ int launch_stft_generic(const TIn* wave, int64_t B, int64_t n, int64_t ld, int64
     const size_t smem = sizeof(float2) * 3 * (N / 2);
     auto k = gss::gen::stft_kernel<TIn>;
     if (int rc = prep(k, smem)) return rc;
-    if (B > 65535) return fail(GSS_EUNSUPPORTED, "generic stft: B=%lld > 65535 rows per launch", (long long)B);
-    dim3 grid((unsigned)((T + a.fpc - 1) / a.fpc), (unsigned)B);
-    k<<<grid, gss::gen::THREADS, smem, st>>>(a);
-    return after_launch("gen::stft_kernel");
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {                  // grid.y holds 65535 rows: longer batches take several launches
+        const int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
+        gss::gen::StftArgs c = a;
+        c.wave = wave + b0 * ld; c.feat = feat + b0 * T * N; c.B = nb;
+        dim3 grid((unsigned)((T + a.fpc - 1) / a.fpc), (unsigned)nb);
+        k<<<grid, gss::gen::THREADS, smem, st>>>(c);
+        if (int rc = after_launch("gen::stft_kernel")) return rc;
+    }
+    return GSS_OK;
 }
 
 template <bool FROM_WAVE>
@@ -222,11 +275,20 @@ int launch_ola_generic(gss::gen::OlaArgs a, cudaStream_t st) {
     const size_t smem = sizeof(float2) * 3 * (a.N / 2) + sizeof(float) * 2 * span;
     auto k = gss::gen::ola_kernel<FROM_WAVE>;
     if (int rc = prep(k, smem)) return rc;
-    if (a.rows > 65535) return fail(GSS_EUNSUPPORTED, "generic istft: %lld rows > 65535 per launch", (long long)a.rows);
     const int64_t hops = (a.T - 1) + R / 2;
-    dim3 grid((unsigned)((hops + a.ft - 1) / a.ft), (unsigned)a.rows);
-    k<<<grid, gss::gen::THREADS, smem, st>>>(a);
-    return after_launch("gen::ola_kernel");
+    const int S = FROM_WAVE ? a.S : 1;
+    const int64_t per = 65535 - 65535 % S;                        // grid.y holds 65535 rows; a chunk keeps whole mixtures
+    for (int64_t r0 = 0; r0 < a.rows; r0 += per) {
+        gss::gen::OlaArgs c = a;
+        c.rows = a.rows - r0 < per ? a.rows - r0 : per;
+        c.out = a.out + r0 * a.ld_out;
+        if (FROM_WAVE) { c.wave = a.wave + (r0 / S) * a.ld; c.mask = a.mask + r0 * a.T * (a.N / 2); }
+        else c.feat = a.feat + r0 * a.T * a.N;
+        dim3 grid((unsigned)((hops + a.ft - 1) / a.ft), (unsigned)c.rows);
+        k<<<grid, gss::gen::THREADS, smem, st>>>(c);
+        if (int rc = after_launch("gen::ola_kernel")) return rc;
+    }
+    return GSS_OK;
 }
 
 #endif  // GSS_HAS(0)
@@ -235,7 +297,7 @@ int launch_ola_generic(gss::gen::OlaArgs a, cudaStream_t st) {
 template <typename K>
 int64_t cta_slots(K kernel, int threads, size_t smem) {
     int nb = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    if (kernel_info((const void*)kernel, threads, smem, &nb) != GSS_OK) nb = 1;
     return (int64_t)sm_count() * nb;
 }
 template <int N> size_t team_bytes(int nbuf) { return sizeof(float2) * (size_t)nbuf * (N + N / gss::team::Plan<N>::R0); }
@@ -1022,6 +1084,60 @@ int gss_gather_rows_i16(const int16_t* flat, const int64_t* offsets, const int64
     if (B == 0) return GSS_OK;
     gss::gather_rows_i16_kernel<<<grid_for(B * ld, 256), 256, 0, (cudaStream_t)stream>>>(flat, offsets, lengths, idx, B, ld, out);
     return after_launch("gather_rows_i16_kernel");
+}
+
+// ---- A14: scipy.signal.resample (main.py:89-95) ------------------------------------------------------
+static int64_t resample_m(int64_t n, int64_t num) { return gss::rs::pow2_at_least(2 * (n > num ? n : num) - 1); }
+size_t gss_resample_workspace_bytes(int64_t n, int64_t num) {
+    if (n < 1 || num < 1 || n > ((int64_t)1 << 30) || num > ((int64_t)1 << 30)) return 0;
+    return sizeof(double2) * (size_t)(4 * resample_m(n, num) + n + 2 * num);
+}
+// power-of-two Stockham FFT, ping-pong between p and q; returns the buffer that holds the result
+static double2* rs_fft(double2* p, double2* q, int64_t M, int sign, cudaStream_t st) {
+    const int grid = grid_for(M / 2, 256);
+    for (int64_t Ns = 1; Ns < M; Ns <<= 1) {
+        gss::rs::fft_pass_kernel<<<grid, 256, 0, st>>>(p, q, M, Ns, sign);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        double2* t = p; p = q; q = t;
+    }
+    return p;
+}
+// length-L DFT (sign -1) or unnormalised inverse DFT (sign +1) of `in` (real or complex) into out[L], by Bluestein
+static int rs_bluestein(const double* in_re, const double2* in_c, int64_t L, int sign, double2* out,
+                        double2* a0, double2* a1, double2* b0, double2* b1, cudaStream_t st) {
+    const int64_t M = gss::rs::pow2_at_least(2 * L - 1);
+    const int gm = grid_for(M, 256);
+    if (in_re) gss::rs::prepare_kernel<true><<<gm, 256, 0, st>>>(in_re, nullptr, L, M, sign, a0, b0);
+    else gss::rs::prepare_kernel<false><<<gm, 256, 0, st>>>(nullptr, in_c, L, M, sign, a0, b0);
+    if (int rc = after_launch("rs::prepare_kernel")) return rc;
+    double2* pa = rs_fft(a0, a1, M, -1, st);
+    double2* pb = rs_fft(b0, b1, M, -1, st);
+    gss::rs::pointwise_kernel<<<gm, 256, 0, st>>>(pa, pb, M);
+    if (int rc = after_launch("rs::pointwise_kernel")) return rc;
+    double2* pc = rs_fft(pa, pa == a0 ? a1 : a0, M, +1, st);
+    gss::rs::finish_kernel<<<grid_for(L, 256), 256, 0, st>>>(pc, L, M, sign, out);
+    return after_launch("rs::finish_kernel");
+}
+int gss_resample_f64(const double* x, int64_t rows, int64_t n, int64_t ld, int64_t num, double* y, int64_t ld_y,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x || !y || !workspace) return fail(GSS_EINVAL, "resample: null pointer");
+    if (rows < 0 || n < 1 || num < 1 || ld < n || ld_y < num) return fail(GSS_EINVAL, "resample: bad shape rows=%lld n=%lld num=%lld", (long long)rows, (long long)n, (long long)num);
+    const size_t need = gss_resample_workspace_bytes(n, num);
+    if (!need) return fail(GSS_EUNSUPPORTED, "resample: lengths above 2^30 are not supported");
+    if (workspace_bytes < need || ((uintptr_t)workspace & 15)) return fail(GSS_EINVAL, "resample: workspace of %zu bytes (16-byte aligned) needed, got %zu", need, workspace_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t M = resample_m(n, num);
+    double2* a0 = (double2*)workspace; double2* a1 = a0 + M; double2* b0 = a1 + M; double2* b1 = b0 + M;
+    double2* X = b1 + M; double2* Y = X + n; double2* Z = Y + num;
+    for (int64_t r = 0; r < rows; ++r) {
+        if (int rc = rs_bluestein(x + r * ld, nullptr, n, -1, X, a0, a1, b0, b1, st)) return rc;          // rfft (all n bins)
+        gss::rs::resize_kernel<<<grid_for(num, 256), 256, 0, st>>>(X, n, num, Y);
+        if (int rc = after_launch("rs::resize_kernel")) return rc;
+        if (int rc = rs_bluestein(nullptr, Y, num, +1, Z, a0, a1, b0, b1, st)) return rc;                // irfft (Hermitian spectrum)
+        gss::rs::real_scale_kernel<<<grid_for(num, 256), 256, 0, st>>>(Z, num, 1.0 / (double)n, y + r * ld_y);   // (1/num) * (num/n)
+        if (int rc = after_launch("rs::real_scale_kernel")) return rc;
+    }
+    return GSS_OK;
 }
 
 int gss_wav16_normalise(const float* x, int64_t R, int64_t len, int64_t ld, float* minmax, int16_t* pcm, void* stream) {

@@ -22,6 +22,7 @@
 #ifndef GSS_API_H
 #define GSS_API_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -131,6 +132,16 @@ int gss_mask_istft_feature_ae(const float* feat, const float* mask, int64_t B, i
  * so the all-reduce can follow on the same stream without a host round trip. */
 int gss_metric_finalise(const float* ae_rows, const float* snr, int64_t B, int m, int n, double elems_per_row,
                         float* vec4, void* stream);
+
+/* A14: scipy.signal.resample(x, num) (Fourier method) as main.py:89-95 calls it for files that are not at 16 kHz:
+ * rfft, keep min(n, num)/2 + 1 bins (shared Nyquist bin folded / split as SciPy does for real input), irfft to num
+ * samples, scale num/n.  Arbitrary n and num: both transforms are Bluestein chirp-z transforms over a power-of-two
+ * Stockham FFT, all in float64 (SciPy promotes int16 samples to float64), phases reduced exactly in integers.
+ *   x [rows, ld] f64 -> y [rows, ld_y] f64, num samples per row.  workspace: gss_resample_workspace_bytes(n, num)
+ *   bytes of device memory, 16-byte aligned, owned by the caller. */
+size_t gss_resample_workspace_bytes(int64_t n, int64_t num);
+int gss_resample_f64(const double* x, int64_t rows, int64_t n, int64_t ld, int64_t num, double* y, int64_t ld_y,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Batch assembly for the device-resident corpus that replaces the FFT_SIZE-baked pickles (TIMIT/process.py:80-161,
  * app/datasets/timit.py:47-52): out[r, :] = utterance idx[r] of the flat int16 store, zero-padded to ld samples.

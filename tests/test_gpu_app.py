@@ -430,3 +430,31 @@ def test_waveform_dataset_from_directory(T, ops, hp, tmp_path):
     scipy.io.wavfile.write(os.path.join(tmp_path, "dr1", "e5.wav"), 8000, waves["a1.wav"])
     with pytest.raises(ValueError, match="Sampling rate"):
         WaveformData().add_directory('train', str(tmp_path))
+
+
+def test_resample_long_clip_and_batch(T, ops):
+    """the hand-written Bluestein resampler at demo sizes: 10 s of 44.1 kHz -> 16 kHz, and a small batch of rows"""
+    import scipy.signal
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(441000)
+    got = ops.resample(dev(T, x), 160000).cpu().numpy()
+    assert np.abs(got - scipy.signal.resample(x, 160000)).max() < 1e-11
+    xb = rng.standard_normal((3, 2, 1234))
+    gotb = ops.resample(dev(T, xb), 777).cpu().numpy()
+    assert gotb.shape == (3, 2, 777) and np.abs(gotb - scipy.signal.resample(xb, 777, axis=-1)).max() < 1e-12
+
+
+def test_per_frame_path_takes_more_than_65535_rows(T, ops):
+    """the per-frame kernels (FFT_SIZE 64 / 128) index rows through grid.y: long batches are split into several launches"""
+    N, H, n, B = 64, 32, 96, 70000
+    g = T.Generator(device="cuda").manual_seed(9)
+    x = T.randn(B, n, device="cuda", generator=g) * 0.1
+    f = ops.stft(x, N, H)
+    y = ops.istft(f, H)
+    assert T.equal(f[65535:65540], ops.stft(x[65535:65540].contiguous(), N, H))
+    err = (y[:, :n] - x).double().pow(2).sum() / x.double().pow(2).sum()
+    assert 10 * np.log10(1.0 / float(err)) >= 100.0
+    m = T.rand(B, 2, f.shape[1], N // 2, device="cuda", generator=g)
+    w = ops.mask_istft(x, m, N, H)
+    ref = R.mask_istft_np(x[69999:].cpu().numpy(), m[69999:].cpu().numpy(), N, H).reshape(2, -1)
+    assert R.rel_l2(w.reshape(B, 2, -1)[69999].cpu().numpy(), ref) < REL_L2

@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/../gan_sass_tf_b200/csrc"
 tag=$1; shift
-F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
+F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fno-gnu-unique"
 mkdir -p /tmp/gobj
 for k in 0 1 2 4; do [ -f /tmp/gobj/p$k.o ] || nvcc $F -DGSS_PART=$k -c gss_api.cu -o /tmp/gobj/p$k.o 2>/dev/null & done
 nvcc $F -DGSS_PART=3 "$@" -Xptxas -v -c gss_api.cu -o /tmp/gobj/p3_$tag.o 2>&1 | grep -E "error|Compiling entry|Used|spill" | sed -E 's/ptxas info\s+: //g' \
