@@ -106,6 +106,32 @@ if "--dftgemm" in sys.argv:
     torch.backends.cuda.matmul.allow_tf32 = False
     ours = ops.stft(waves[0], N, H)[:, N // (2 * H): N // (2 * H) + (n - N) // H + 1].reshape(-1, N)
     print(f"   (libgss stft on the same interior frames vs the fp64 GEMM: rel {float((ours.double() - ref64).norm() / ref64.norm()):.1e})")
+    del ref64, ours
+    # synthesis side: packed features [B*T, N] x inverse packed-DFT matrix [N, N] (window folded in) -> windowed frames
+    # [B*T, N]; the overlap-add of those frames (another pass over 4x the output) is NOT included - this favours the GEMM.
+    ck = torch.full((N // 2,), 2.0, device=dev, dtype=torch.float64); ck[0] = 1.0
+    hann = 0.5 - 0.5 * torch.cos(2 * torch.pi * nn / N)
+    Wi = torch.cat([torch.cos(ang).T * ck[:, None], -torch.sin(ang).T * ck[:, None]], dim=0) * (hann * 0.5)[None, :]   # [N, N]: rows = packed slots
+    Wi[N // 2] = torch.cos(torch.pi * nn) * hann * 0.5                                    # the Nyquist slot (rides in Im-DC)
+    Wi = Wi.float().contiguous()
+    Wihi, Wilo = tf32_split(Wi)
+    fm = [f.reshape(-1, N) for f in feat]
+
+    def igemm(i, mode):
+        f = fm[i % 3]
+        if mode == "fp32":
+            torch.backends.cuda.matmul.allow_tf32 = False
+            return f @ Wi
+        torch.backends.cuda.matmul.allow_tf32 = True
+        if mode == "tf32":
+            return f @ Wi
+        fhi, flo = tf32_split(f)
+        return fhi @ Wihi + (fhi @ Wilo + flo @ Wihi)
+    ref64 = fm[0].double() @ Wi.double()
+    for mode in ("fp32", "tf32", "3xtf32"):
+        err = float((igemm(0, mode).double() - ref64).norm() / ref64.norm())
+        timeit(f"iDFT-GEMM cuBLAS {mode} (rel {err:.1e}), no overlap-add", lambda i: igemm(i, mode), 4 * B * (T * N + (T - 1) * H))
+    torch.backends.cuda.matmul.allow_tf32 = False
     del ref64
 x = feat[0]
 from gan_sass_tf_b200.app import hparams
