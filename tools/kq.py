@@ -46,8 +46,12 @@ if "--feat" in sys.argv:
     lg = torch.empty_like(lins[0])
     t_d = timeit(lambda i: ops.stft_dual(waves[i % 3], N, H, out_lin=lins[i % 3], out_log=lg))
     t_f = timeit(lambda i: ops.mask_istft_feature(lins[i % 3], masks[i % 3], H, out=out))
+    rows = torch.zeros(B, device=dev)
+    t_a = timeit(lambda i: ops.mask_istft_feature(lins[i % 3], masks[i % 3], H, out=out, ae_rows=rows))
     ops.mask_istft_feature(lins[0], masks[0], H, out=out)
-    print(f"{tag:24s} {extra:28s} stft_dual {t_d:7.1f} us  mask_istft_feature {t_f:7.1f} us | fp out {out.double().abs().sum().item():.6f}")
+    ref = ops.istft(ops.apply_mask(lins[0][:32], masks[0][:32]), H)
+    err = float((out[:96] - ref).norm() / ref.norm())
+    print(f"{tag:24s} {extra:28s} stft_dual {t_d:7.1f} us  mask_istft_feature {t_f:7.1f} us  +AE {t_a:7.1f} us | fp out {out.double().abs().sum().item():.6f} rel vs unfused {err:.2e}")
 ops.mask_istft(waves[0], masks[0], N, H, out=out)
 f = ops.stft_log(waves[0], N, H)
 print(f"{tag:24s} {extra:28s} stft_log {t_st:7.1f} us  mask_istft {t_sy:7.1f} us  | fp out {out.double().abs().sum().item():.6f} feat {f.double().abs().sum().item():.6f}")
