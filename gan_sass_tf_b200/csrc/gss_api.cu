@@ -354,10 +354,15 @@ int team_synth_feat_st(gss::team::SynthFeatArgs a, cudaStream_t st) {
 }
 template <int N, int HS>
 int team_synth_feat(gss::team::SynthFeatArgs a, cudaStream_t st) {
-    if (a.S % 3 == 0) return team_synth_feat_st<N, HS, 3>(a, st);
-    if (a.S % 2 == 0) return team_synth_feat_st<N, HS, 2>(a, st);
-    if (a.S == 1) return team_synth_feat_st<N, HS, 1>(a, st);
-    return team_synth_feat_st<N, HS, 3>(a, st);
+    // one source per work item where that buys resident CTAs (gss_team.cuh, Plan<N>::FEAT_ST1)
+    if constexpr (gss::team::Plan<N>::FEAT_ST1) {
+        return team_synth_feat_st<N, HS, 1>(a, st);
+    } else {
+        if (a.S % 3 == 0) return team_synth_feat_st<N, HS, 3>(a, st);
+        if (a.S % 2 == 0) return team_synth_feat_st<N, HS, 2>(a, st);
+        if (a.S == 1) return team_synth_feat_st<N, HS, 1>(a, st);
+        return team_synth_feat_st<N, HS, 3>(a, st);
+    }
 }
 // F<N, HS>::run(args...) for the (N, hs) pairs the team kernels cover
 #ifdef GSS_EXPERIMENTAL     // team kernels at 256 / 512 are reachable through gss_set_path(1) only: cross-check builds

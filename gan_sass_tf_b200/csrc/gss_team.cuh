@@ -105,11 +105,16 @@ __device__ __forceinline__ void dftR(float2 (&a)[R]) {
 // (chosen so that nothing spills: the radix-16 butterflies with their expanded twiddles are register-hungry, and a
 // spilling synthesis kernel at 12 warps/SM measured 15 % slower than a clean one at 8)
 template <int N_> struct Plan;
-template <> struct Plan<256>  { static constexpr int R0 = 8,  RM = 4,  MINB = 16, MINB_ISTFT = 16, MINB_SYNTH = 16; };
-template <> struct Plan<512>  { static constexpr int R0 = 8,  RM = 8,  MINB = 8,  MINB_ISTFT = 8,  MINB_SYNTH = 8; };
-template <> struct Plan<1024> { static constexpr int R0 = 16, RM = 4,  MINB = 8,  MINB_ISTFT = 6,  MINB_SYNTH = 4; };
-template <> struct Plan<2048> { static constexpr int R0 = 16, RM = 8,  MINB = 4,  MINB_ISTFT = 3,  MINB_SYNTH = 2; };
-template <> struct Plan<4096> { static constexpr int R0 = 16, RM = 16, MINB = 2,  MINB_ISTFT = 1,  MINB_SYNTH = 1; };
+// MINB_FEAT / FEAT_ST1: the feature-fed synthesis.  At 1024 / 2048 it runs ONE source per work item (the sources of a mixture
+// become separate items that re-read the pair's features, mostly from L2) at 144-168 registers and 6 / 3 resident CTAs per SM:
+// S = 3 at B = 1024 x 3 s 909 -> 778 us and 1042 -> 827 us against three sources per item at 4 / 2 CTAs
+// (profiles/r2_team_st1*.txt); at 4096 (256 threads per CTA) the register cap that a second CTA needs spills, and one
+// source per item at one CTA is slower than three (1069 against 1005 us), so it keeps the grouping of the waveform-fed kernel.
+template <> struct Plan<256>  { static constexpr int R0 = 8,  RM = 4,  MINB = 16, MINB_ISTFT = 16, MINB_SYNTH = 16, MINB_FEAT = 16; static constexpr bool FEAT_ST1 = false; };
+template <> struct Plan<512>  { static constexpr int R0 = 8,  RM = 8,  MINB = 8,  MINB_ISTFT = 8,  MINB_SYNTH = 8,  MINB_FEAT = 8;  static constexpr bool FEAT_ST1 = false; };
+template <> struct Plan<1024> { static constexpr int R0 = 16, RM = 4,  MINB = 8,  MINB_ISTFT = 6,  MINB_SYNTH = 4,  MINB_FEAT = 6;  static constexpr bool FEAT_ST1 = true; };
+template <> struct Plan<2048> { static constexpr int R0 = 16, RM = 8,  MINB = 4,  MINB_ISTFT = 3,  MINB_SYNTH = 2,  MINB_FEAT = 3;  static constexpr bool FEAT_ST1 = true; };
+template <> struct Plan<4096> { static constexpr int R0 = 16, RM = 16, MINB = 2,  MINB_ISTFT = 1,  MINB_SYNTH = 1,  MINB_FEAT = 1;  static constexpr bool FEAT_ST1 = false; };
 
 template <int N_, int HS_>
 struct TGeo {
@@ -638,7 +643,7 @@ template <int N> constexpr size_t synth_feat_bytes() {
 
 // resident CTAs per SM the feature-fed kernel is compiled for (tuning macro; default = the waveform-fed kernel's)
 #ifndef GSS_TEAM_FEAT_MINB
-#define GSS_TEAM_FEAT_MINB(N) Plan<N>::MINB_SYNTH
+#define GSS_TEAM_FEAT_MINB(N) Plan<N>::MINB_FEAT
 #endif
 template <int N, int HS, int ST>
 __global__ void __launch_bounds__(TGeo<N, HS>::TPT, GSS_TEAM_FEAT_MINB(N)) mask_istft_feat_kernel(const SynthFeatArgs p) {
