@@ -245,6 +245,7 @@ class Step:
         self.ev_reduced = [torch.cuda.Event() for _ in range(2)]
         self.reduced_once = [False, False]
         self.lib = _native.lib()
+        self.fused_metric = self.N in (256, 512)          # the fused auto-encoder partial exists in the register-exchange kernels
 
     def feature(self, i, ev=None):
         """stft_dual -> mask_istft_feature (+ fused AE partial) -> metric vector (-> all-reduce on the side stream)"""
@@ -257,9 +258,11 @@ class Step:
         if ev:
             ev[1].record(self.stream)
         nv.check(lib.gss_mask_istft_feature_ae(self.lin[k].data_ptr(), self.masks[k].data_ptr(), B, S, T, N, H, nv.FLAG_REVERSE,
-                                               self.out.data_ptr(), L, self.ae_rows.data_ptr(), st))
+                                               self.out.data_ptr(), L, self.ae_rows.data_ptr() if self.fused_metric else None, st))
         if ev:
             ev[2].record(self.stream)
+        if not self.fused_metric:
+            return
         if self.comm is not None and self.reduced_once[v]:
             self.stream.wait_event(self.ev_reduced[v])             # the all-reduce of step i-2 has consumed this vector
         nv.check(lib.gss_metric_finalise(self.ae_rows.data_ptr(), None, B, 1, 1, float(T * N), self.vec[v].data_ptr(), st))
@@ -479,6 +482,33 @@ def run_native(args):
         del sc
         torch.cuda.empty_cache()
 
+    # ---- C5 (FFT_SIZE sweep, B = 1024 x 3 s, hop N/4) and C3 (one 60 s clip, FFT 1024 / hop 256): one GPU only ----
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = {"what": "BASELINE configs 5 and 3 through the same step (stft_dual + mask_istft_feature, S = 3; the fused metric "
+                         "exists for 256 / 512 only), device-resident, 10 steps after 3 warm-ups each", "unit": UNIT, "c5": {}, "c3": None}
+        peak_gbs = 6552.6
+        try:
+            peak_gbs = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak_gbs))
+        except Exception:
+            pass
+        cases = [("c5", dict(B=1024, n=48000, N=Nf, H=Nf // 4, S=3)) for Nf in (256, 512, 1024, 2048, 4096)]
+        cases.append(("c3", dict(B=1, n=960000, N=1024, H=256, S=3)))
+        keep = sp
+        for tag, wc in cases:
+            sp = Step(torch, dist, wc, dev, rank, world, 2, 77)
+            ms, k1, k2, _, _ = timed(sp.feature, 10, 3)
+            sb, yb = algorithmic_bytes(wc["B"], wc["n"], wc["N"], wc["H"], wc["S"])
+            row = {"ms_per_step": ms / 10, "analysis_ms": k1, "synthesis_ms": k2, "value": wc["B"] * wc["n"] / SR / (ms / 10 * 1e-3),
+                   "step_frac_of_hbm": (sb + yb) / (ms / 10 * 1e-3) / 1e9 / peak_gbs, "synthesis_frac_of_hbm": yb / (k2 * 1e-3) / 1e9 / peak_gbs}
+            if tag == "c5":
+                sweep["c5"][str(wc["N"])] = row
+            else:
+                sweep["c3"] = dict(row, us_per_clip=ms / 10 * 1e3, note="one clip: launch- and latency-bound (58 MB of algorithmic bytes)")
+            del sp
+            torch.cuda.empty_cache()
+        sp = keep
+
     t = torch.tensor([total_ms, e2e_ms, stft_ms, synth_ms, e2e16_ms, alt_ms, link_ms,
                       sustained["seconds"] * 1e3 if sustained else float("nan")], device=dev, dtype=torch.float64)
     if world > 1:
@@ -549,6 +579,7 @@ def run_native(args):
                 "h2d_bytes_per_step": B * n * 2, "d2h_bytes_per_step": B * S * L * 2,
                 "what": "same loop, int16 PCM in / per-clip normalised int16 PCM out (SpectralPipeline(pcm16=True))"},
             "c4": c4,
+            "sweep": sweep,
             "gpu_launches": int(launches),
             "collective": None if world == 1 else {
                 "what": "one NCCL all-reduce (sum) of the 4-float metric vector per step, on a side stream behind the step's metric kernel, "
@@ -605,6 +636,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (8192 x 4 s) block")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the C5 / C3 block (one-GPU runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

@@ -3,7 +3,7 @@
 #   gpurun --timeout 900 -- 'bash tools/profile_r2.sh r2e'
 set -u
 TAG=${1:-r2e}
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-c4 --no-sustained"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-c4 --no-sustained --no-sweep"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
