@@ -167,3 +167,50 @@ def test_cluster_reductions_match_oracle(T, ops, B, m, n, L):
     pcm = ops.wav16_normalise(dev(T, clear.reshape(B * m, L))).cpu().numpy()
     refp = np.stack([R.wav16_normalise(r) for r in clear.reshape(B * m, L)])
     assert np.abs(pcm.astype(np.int32) - refp.astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("N,H", [(512, 128), (1024, 256)])
+def test_bench_step_in_a_cuda_graph(T, ops, N, H):
+    """the round-2 step (dual STFT, feature-fed synthesis with its memset node and fused partial, metric vector, and the
+    cluster-launched cross-SNR) only enqueues on the caller's stream: captured once, replayed on new data."""
+    n, B, S = 9000, 4, 3
+    Tn, _ = R.frame_count(n, N, H)
+    x = T.zeros(B, n, device="cuda")
+    m = T.zeros(B, S, Tn, N // 2, device="cuda")
+    lin = T.empty(B, Tn, N, device="cuda"); lg = T.empty(B, Tn, N, device="cuda")
+    out = T.empty(B * S, (Tn - 1) * H, device="cuda")
+    rows = T.zeros(B, device="cuda") if N == 512 else None
+    vec = T.zeros(4, device="cuda")
+    src = T.zeros(B, 2, Tn, N, device="cuda")
+
+    def step():
+        ops.stft_dual(x, N, H, out_lin=lin, out_log=lg)
+        ops.mask_istft_feature(lin, m, H, out=out, ae_rows=rows)
+        sep = ops.apply_mask(lin, m)
+        snr = ops.batch_cross_snr(src, sep.reshape(B, S, Tn, N))
+        ops.metric_vector(ae_rows=rows, snr=snr, elems_per_row=Tn * N, out=vec)
+        return snr
+    step()                                                             # first call: table fill, attribute opt-ins
+    T.cuda.synchronize()
+    g = T.cuda.CUDAGraph()
+    with T.cuda.graph(g):
+        snr = step()
+    rng = np.random.default_rng(7)
+    for seed in (1, 2):
+        xs = (np.random.default_rng(seed).standard_normal((B, n)) * 0.1).astype(np.float32)
+        ms = rng.random((B, S, Tn, N // 2)).astype(np.float32)
+        ss = (rng.standard_normal((B, 2, Tn, N)) * 0.01).astype(np.float32)
+        x.copy_(dev(T, xs)); m.copy_(dev(T, ms)); src.copy_(dev(T, ss))
+        g.replay()
+        T.cuda.synchronize()
+        ref_lin = R.stft_feature_np(xs, N, H, np.float64, np.float64)
+        assert R.rel_l2(lin.cpu().numpy(), ref_lin) < REL_L2
+        assert R.rel_l2(out.cpu().numpy(), R.mask_istft_np(xs, ms, N, H).reshape(B * S, -1)) < REL_L2
+        sep64 = R.apply_mask(ref_lin, ms.astype(np.float64)).reshape(B, S, Tn, N)
+        ref_snr = R.batch_cross_snr(ss.astype(np.float64), sep64)
+        np.testing.assert_allclose(snr.cpu().numpy(), ref_snr, atol=2e-3)
+        v = vec.cpu().numpy()
+        assert abs(v[0] / B - ref_snr.max(axis=2).mean()) < 2e-3 and v[3] == B
+        if rows is not None:
+            ref_ae = R.autoencoder_loss(sep64.reshape(B * S, Tn, N), ref_lin, B, S)
+            assert abs(v[1] / B - ref_ae) <= 2e-5 * abs(ref_ae)
