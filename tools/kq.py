@@ -6,7 +6,7 @@ import torch
 from gan_sass_tf_b200.app import ops
 from gan_sass_tf_b200 import _native
 
-N, H, B, n, S = 512, 128, 256, 48000, 3
+N, H, B, n, S = 512, 128, int(os.environ.get('KQ_B', 256)), int(os.environ.get('KQ_n', 48000)), 3
 T, _ = _native.frame_count(n, N, H)
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
