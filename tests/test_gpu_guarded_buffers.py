@@ -112,3 +112,38 @@ def test_elementwise_and_reduction_kernels_stay_inside(T, ops):
         assert all(bool(T.isfinite(o).all()) for o in outs)
     finally:
         hparams.FFT_SIZE = old
+
+
+@pytest.mark.parametrize("N,H", [(512, 128), (256, 64), (1024, 256)])
+def test_results_do_not_depend_on_timing(T, ops, N, H):
+    """Poor man's racecheck for the shared-memory stages (TMA refills behind team barriers, double-buffered mask stage,
+    single feature stage): the same launch repeated under different contention - alone, next to a bandwidth hog on another
+    stream, next to another instance of itself - must give identical bits every time."""
+    from gan_sass_tf_b200 import _native
+    n, B, S = 24000, 48, 3
+    g = T.Generator(device="cuda").manual_seed(N)
+    Tn, _ = _native.frame_count(n, N, H)
+    x = T.randn(B, n, device="cuda", generator=g) * 0.1
+    m = T.rand(B, S, Tn, N // 2, device="cuda", generator=g)
+    lin = ops.stft(x, N, H)
+    ref_f = ops.mask_istft_feature(lin, m, H)
+    ref_w = ops.mask_istft(x, m, N, H)
+    ref_s = ops.stft_log(x, N, H)
+    hog_a = T.empty(64 << 20, device="cuda"); hog_b = T.empty(64 << 20, device="cuda")
+    side = T.cuda.Stream()
+    for rep in range(24):
+        mode = rep % 3
+        if mode == 1:
+            with T.cuda.stream(side):
+                for _ in range(4):
+                    hog_b.copy_(hog_a)
+        elif mode == 2:
+            with T.cuda.stream(side):
+                other = ops.mask_istft_feature(lin, m, H)
+        out_f = ops.mask_istft_feature(lin, m, H, reverse=bool(rep & 1))
+        out_w = ops.mask_istft(x, m, N, H)
+        out_s = ops.stft_log(x, N, H)
+        T.cuda.synchronize()
+        assert T.equal(out_f, ref_f) and T.equal(out_w, ref_w) and T.equal(out_s, ref_s), f"repetition {rep} differs"
+        if mode == 2:
+            assert T.equal(other, ref_f)
