@@ -594,7 +594,8 @@ int synth_feat_by_s(gss::SynthArgs a, cudaStream_t st) {
         return fail(GSS_EUNSUPPORTED, "mask_istft_feature: the fused auto-encoder partial needs S <= 3 (S = 4 at hop N/4 only), got S=%d", a.S);
     }
     if (a.S % 3 == 0) return launch_synth_w<N, HS, 3, 4, true>(a, st);
-    if constexpr (HS == 2) { if (a.S % 4 == 0) return launch_synth_w<N, HS, 4, 4, true>(a, st); }
+    // S = 4, 8: two sources per pass (four per pass need 118 KB of shared memory per CTA with the feature stage: one CTA per SM,
+    // 268.8 us against 2 x 113 us at C2 size; profiles/r2_s_sweep.txt) - four per pass only for the fused auto-encoder partial above
     if (a.S % 2 == 0) return launch_synth_w<N, HS, 2, 4, true>(a, st);
     if (a.S == 1) return launch_synth_w<N, HS, 1, 4, true>(a, st);
     return launch_synth_w<N, HS, 3, 4, true>(a, st);
