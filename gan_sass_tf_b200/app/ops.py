@@ -331,7 +331,7 @@ def mask_istft_feature(mix_feature, mask, hop=None, out=None, reverse=False, ae_
     last-to-first (a cache hint when ``mix_feature`` was written just before; results are identical).
     ``ae_rows`` (float32 ``[B]`` on the device): also receives the per-mixture auto-encoder partial
     ``sum((sum_s separated_s - mixed)^2)`` of main.py:353-361, computed inside the same kernel (FFT_SIZE 256 / 512,
-    S <= 3 or S = 4 at hop N/4; ``ValueError`` otherwise - use ``ae_loss(apply_mask(...))`` there).
+    S <= 4 (S <= 3 at hop N/8); ``ValueError`` otherwise - use ``ae_loss(apply_mask(...))`` there).
     Differentiable in both arguments."""
     _dev(mix_feature, "mask_istft_feature"); _dev(mask, "mask_istft_feature")
     assert mix_feature.dim() == 3 and mask.dim() == 4, "mask_istft_feature: feature [B,T,N], mask [B,S,T,N/2]"

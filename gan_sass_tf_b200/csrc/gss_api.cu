@@ -590,8 +590,10 @@ int synth_feat_by_s(gss::SynthArgs a, cudaStream_t st) {
         if (a.S == 3) return launch_synth_w<N, HS, 3, 4, true, true>(a, st);
         if (a.S == 2) return launch_synth_w<N, HS, 2, 4, true, true>(a, st);
         if (a.S == 1) return launch_synth_w<N, HS, 1, 4, true, true>(a, st);
-        if constexpr (HS == 2) { if (a.S == 4) return launch_synth_w<N, HS, 4, 4, true, true>(a, st); }
-        return fail(GSS_EUNSUPPORTED, "mask_istft_feature: the fused auto-encoder partial needs S <= 3 (S = 4 at hop N/4 only), got S=%d", a.S);
+        // S = 4 (the reference's default MAX_N_SIGNAL + 1, main.py:346): all four sources in one pass, in CTAs of two warps so
+        // that the 29 KB of stages per warp still leave three CTAs per SM
+        if constexpr (HS >= 2) { if (a.S == 4) return launch_synth_w<N, HS, 4, 2, true, true>(a, st); }
+        return fail(GSS_EUNSUPPORTED, "mask_istft_feature: the fused auto-encoder partial needs S <= 4 (S <= 3 at hop N/8), got S=%d", a.S);
     }
     if (a.S % 3 == 0) return launch_synth_w<N, HS, 3, 4, true>(a, st);
     // S = 4, 8: two sources per pass (four per pass need 118 KB of shared memory per CTA with the feature stage: one CTA per SM,

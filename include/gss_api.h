@@ -121,8 +121,8 @@ int gss_mask_istft_feature(const float* feat, const float* mask, int64_t B, int 
 /* Same, and the auto-encoder loss partial of main.py:353-361 from the registers that already hold the spectrum and the
  * gains: ae_rows[b] = sum over the packed elements of mixture b of ((sum_s mask_s - 1) * feature)^2, i.e.
  * sum((sum_s separated_s - mixed)^2) for separated_s = mask_s * mixed; the loss is sum_b ae_rows[b] / (B*T*N).
- * ae_rows [B] f32 is zeroed by the call (a memset node on `stream`).  FFT_SIZE 256 / 512 and S <= 3 (S = 4 at hop
- * N/4); other shapes return GSS_EUNSUPPORTED (use gss_apply_mask + gss_ae_partial).  ae_rows = NULL: plain call. */
+ * ae_rows [B] f32 is zeroed by the call (a memset node on `stream`).  FFT_SIZE 256 / 512 and S <= 4 (S <= 3 at hop
+ * N/8); other shapes return GSS_EUNSUPPORTED (use gss_apply_mask + gss_ae_partial).  ae_rows = NULL: plain call. */
 int gss_mask_istft_feature_ae(const float* feat, const float* mask, int64_t B, int S, int64_t T, int N, int H, int flags,
                               float* out, int64_t ld_out, float* ae_rows, void* stream);
 

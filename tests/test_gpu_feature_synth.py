@@ -118,7 +118,8 @@ def test_feature_entry_rejects_bad_args(T, ops):
 
 
 @pytest.mark.parametrize("N,H,n,B,S", [(512, 128, 9000, 3, 3), (512, 128, 48000, 2, 3), (512, 256, 5000, 2, 2), (512, 64, 4000, 1, 1),
-                                       (512, 128, 6001, 2, 4), (256, 128, 5000, 4, 3), (256, 64, 3000, 2, 4)])
+                                       (512, 128, 6001, 2, 4), (256, 128, 5000, 4, 3), (256, 64, 3000, 2, 4),
+                                       (256, 128, 16256, 8, 4), (512, 256, 9000, 3, 4)])      # the reference's defaults: S = 4 at hop N/2
 def test_fused_autoencoder_partial(T, ops, N, H, n, B, S):
     """ae_rows from inside the synthesis kernel == main.py:353-361 on the masked features (oracle: NumPy float64)."""
     rng = np.random.default_rng(N + n + S)

@@ -82,7 +82,7 @@ def test_kernels_stay_inside_their_buffers(T, ops, N, H, n, B, S):
         assert T.equal(lin, lin_ref) and T.equal(lg, lg_ref)
         ops.mask_istft_feature(lin, m, H, out=wf)
         assert T.equal(wf, wf_ref)
-        if N <= 512 and (S <= 3 or (S == 4 and 4 * H == N)):
+        if N <= 512 and (S <= 3 or (S == 4 and 8 * H != N)):
             rows.fill_(float("nan"))
             ops.mask_istft_feature(lin, m, H, out=wf, ae_rows=rows)
             assert T.equal(wf, wf_ref) and bool(T.isfinite(rows).all())
