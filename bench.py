@@ -482,6 +482,24 @@ def run_native(args):
         del sc
         torch.cuda.empty_cache()
 
+    # ---- the collective alone: latency of one 16-byte all-reduce, back to back on the compute stream (N > 1) ----
+    coll_us = None
+    if world > 1:
+        v4 = torch.zeros(4, device=dev)
+        for _ in range(5):
+            dist.all_reduce(v4)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = 200
+        c0.record(stream)
+        for _ in range(nrep):
+            dist.all_reduce(v4)
+        c1.record(stream)
+        barrier()
+        tc = torch.tensor([c0.elapsed_time(c1) / nrep * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        coll_us = float(tc[0])
+
     # ---- C5 (FFT_SIZE sweep, B = 1024 x 3 s, hop N/4) and C3 (one 60 s clip, FFT 1024 / hop 256): one GPU only ----
     sweep = None
     if world == 1 and not args.no_sweep:
@@ -583,7 +601,10 @@ def run_native(args):
             "gpu_launches": int(launches),
             "collective": None if world == 1 else {
                 "what": "one NCCL all-reduce (sum) of the 4-float metric vector per step, on a side stream behind the step's metric kernel, "
-                        "overlapping the next step; the timed region ends after the last one has landed", "per_step": 1},
+                        "overlapping the next step; the timed region ends after the last one has landed", "per_step": 1,
+                "allreduce_latency_us": coll_us,
+                "latency_what": "one 16-byte NCCL all-reduce, 200 back to back on the compute stream, CUDA events, max over ranks: what "
+                                "every step would pay if the collective were serialised with the kernels instead of hidden under the next step"},
             "clocks": clocks,
             "check": {"recon_snr_db": true_snr_db, "ae_loss_mean": ae_mean, "ae_count": ae_count if ae_vec is not None else None,
                       "e2e_checksum": e2e_checksum, "utterances": nchk,
