@@ -99,6 +99,13 @@ int after_launch(const char* name) {
     return GSS_OK;
 }
 
+#ifdef GSS_TUNE
+int tune(const char* name, int dflt) {      // tuning builds only: kernel variants picked by environment variables
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+#endif
+
 int sm_count() {
     static int sms[64]; static std::once_flag once;
     std::call_once(once, [] { for (int& s : sms) s = 0; });
@@ -393,17 +400,14 @@ int launch_stft_w(gss::StftArgs<TIn> a, cudaStream_t st) {
     if (int rc = prep(k, smem)) return rc;
     if (int rc = ensure_tables<N>(st)) return rc;
     gss::ChunkPlan pl = plan_chunks(a.B, a.npairs, 0, team_slots(k, WARPS, TEAMS, smem));
+#ifdef GSS_TUNE
+    if (int nc = tune("GSS_STFT_NCHUNK", 0)) { pl.nchunk = nc; pl.ppc = (a.npairs + nc - 1) / nc; pl.nchunk = (a.npairs + pl.ppc - 1) / pl.ppc; }
+#endif
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.B * a.nchunk;
     k<<<(unsigned)((items + TEAMS - 1) / TEAMS), WARPS * 32, smem, st>>>(a);
     return after_launch("stft_kernel");
 }
-#ifdef GSS_TUNE
-int tune(const char* name, int dflt) {      // tuning builds only: kernel variants picked by environment variables
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-#endif
 template <int N, int HS, bool LOG, typename TIn>
 int launch_stft(gss::StftArgs<TIn> a, cudaStream_t st) {
 #ifdef GSS_TUNE
@@ -483,6 +487,9 @@ int launch_synth_w(gss::SynthArgs a, cudaStream_t st) {
     a.timing = tbuf;
 #endif
     gss::ChunkPlan pl = plan_chunks(a.B * a.ngroups, a.npairs, gss::SGeo<N, HS>::HALO, team_slots(k, WARPS, TEAMS, smem));
+#ifdef GSS_TUNE
+    if (int nc = tune("GSS_SYNTH_NCHUNK", 0)) { pl.nchunk = nc; pl.ppc = (a.npairs + nc - 1) / nc; pl.nchunk = (a.npairs + pl.ppc - 1) / pl.ppc; }
+#endif
     a.ppc = pl.ppc; a.nchunk = pl.nchunk;
     int64_t items = a.B * a.ngroups * a.nchunk;
     k<<<(unsigned)((items + TEAMS - 1) / TEAMS), WARPS * 32, smem, st>>>(a);
