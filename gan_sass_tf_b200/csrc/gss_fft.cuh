@@ -25,6 +25,9 @@
 #ifndef GSS_TW1_FULL
 #define GSS_TW1_FULL 1
 #endif
+#ifndef GSS_E1_V2
+#define GSS_E1_V2 0                  // experiment: second exchange of the N = 512 transform with 64-bit accesses on both sides
+#endif
 
 namespace gss {
 
@@ -128,6 +131,7 @@ struct Geo {
     static constexpr int E0_PLANE = 8 * P0;   // v2 per plane
     static constexpr int E0_F4 = 8 * P0;      // float4-equivalents (both planes)
     static constexpr int E1_PLANE = 8 * P1;   // floats per plane
+    static constexpr int E1V_PLANE = 4 * P1;  // v2 per plane in the [q][column] pair layout (GSS_E1_V2): same bytes
     static constexpr int TEAM_FLOATS = E0_F4 * 4 + 2 * E1_PLANE;
     static_assert(M == 8 || M == 4, "implemented: N = 512 (M = 8, one warp per transform) and N = 256 (M = 4, half a warp); "
                                     "1024 is wired in fft_model.py only");
@@ -286,17 +290,29 @@ __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
             a[n1].im = c.e0[G::E0_PLANE + k0 * G::P0 + 4 * n1 + q];
         }
         dft8<false>(a);
+        GSS_MID_TW(c, w);
+#if GSS_E1_V2
+        // E1 as planes of v2 = (n2 = 2q, n2 = 2q + 1) pairs, [q][column] with pitch P1: the middle pass stores its packed
+        // values as they are (64-bit), bank pairs (4q + k0 + 8 k1) mod 16 are distinct over a half-warp
+        v2* e1v = reinterpret_cast<v2*>(c.e1) + q * G::P1 + k0;
+        e1v[0] = a[0].re; e1v[G::E1V_PLANE] = a[0].im;
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) {
+            cv2 t = cmul<false>(a[k1], w[k1]);
+            e1v[8 * k1] = t.re; e1v[8 * k1 + G::E1V_PLANE] = t.im;
+        }
+#else
         float* re0 = c.e1 + (2 * q) * G::P1 + k0;
         float* re1 = re0 + G::P1;
         re0[0] = a[0].re.x; re1[0] = a[0].re.y;
         re0[G::E1_PLANE] = a[0].im.x; re1[G::E1_PLANE] = a[0].im.y;
-        GSS_MID_TW(c, w);
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) {
             cv2 t = cmul<false>(a[k1], w[k1]);
             re0[8 * k1] = t.re.x; re1[8 * k1] = t.re.y;
             re0[8 * k1 + G::E1_PLANE] = t.im.x; re1[8 * k1 + G::E1_PLANE] = t.im.y;
         }
+#endif
     } else {                     // M = 4: two packed DFT-4 over n1, for k0 = j/4 and j/4 + 4
         const int kb = j >> 2, q = j & 3;
         const cv2 w3 = cmul<false>(c.tw1[0], c.tw1[1]);
@@ -325,11 +341,25 @@ __device__ __forceinline__ void fft_forward(const TeamCtx<N>& c, cv2 (&a)[8]) {
         }
     }
     team_sync(c);
+#if GSS_E1_V2
+    if constexpr (G::M == 8) {
+        const v2* e1v = reinterpret_cast<const v2*>(c.e1);
 #pragma unroll
-    for (int n2 = 0; n2 < 8; ++n2) {
-        const float* p = c.e1 + n2 * G::P1;
-        a[n2].re = make_float2(p[c.cA], p[c.cB]);
-        a[n2].im = make_float2(p[c.cA + G::E1_PLANE], p[c.cB + G::E1_PLANE]);
+        for (int q = 0; q < 4; ++q) {       // column loads as (n2 = 2q, 2q + 1) pairs, then a 2 x 2 transpose into (column A, column B) lanes
+            const v2 ar = e1v[q * G::P1 + c.cA], br = e1v[q * G::P1 + c.cB];
+            const v2 ai = e1v[G::E1V_PLANE + q * G::P1 + c.cA], bi = e1v[G::E1V_PLANE + q * G::P1 + c.cB];
+            a[2 * q].re = make_float2(ar.x, br.x); a[2 * q + 1].re = make_float2(ar.y, br.y);
+            a[2 * q].im = make_float2(ai.x, bi.x); a[2 * q + 1].im = make_float2(ai.y, bi.y);
+        }
+    } else
+#endif
+    {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {
+            const float* p = c.e1 + n2 * G::P1;
+            a[n2].re = make_float2(p[c.cA], p[c.cB]);
+            a[n2].im = make_float2(p[c.cA + G::E1_PLANE], p[c.cB + G::E1_PLANE]);
+        }
     }
     dft8<false>(a);
 }
@@ -345,20 +375,44 @@ __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8], Ho
     const int j = c.j;
     team_sync(c);   // the previous transform's last read of the exchange buffers
     dft8<true>(a);
+#if GSS_E1_V2
+    if constexpr (G::M == 8) {
+        v2* e1v = reinterpret_cast<v2*>(c.e1);
 #pragma unroll
-    for (int n2 = 0; n2 < 8; ++n2) {
-        float* p = c.e1 + n2 * G::P1;
-        p[c.cA] = a[n2].re.x; p[c.cB] = a[n2].re.y;
-        p[c.cA + G::E1_PLANE] = a[n2].im.x; p[c.cB + G::E1_PLANE] = a[n2].im.y;
+        for (int q = 0; q < 4; ++q) {       // 2 x 2 transposes into (n2 = 2q, 2q + 1) pairs per column, 64-bit stores
+            e1v[q * G::P1 + c.cA] = make_float2(a[2 * q].re.x, a[2 * q + 1].re.x);
+            e1v[q * G::P1 + c.cB] = make_float2(a[2 * q].re.y, a[2 * q + 1].re.y);
+            e1v[G::E1V_PLANE + q * G::P1 + c.cA] = make_float2(a[2 * q].im.x, a[2 * q + 1].im.x);
+            e1v[G::E1V_PLANE + q * G::P1 + c.cB] = make_float2(a[2 * q].im.y, a[2 * q + 1].im.y);
+        }
+    } else
+#endif
+    {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {
+            float* p = c.e1 + n2 * G::P1;
+            p[c.cA] = a[n2].re.x; p[c.cB] = a[n2].re.y;
+            p[c.cA + G::E1_PLANE] = a[n2].im.x; p[c.cB + G::E1_PLANE] = a[n2].im.y;
+        }
     }
     team_sync(c);
     if constexpr (G::M == 8) {
         const int k0 = j >> 2, q = j & 3;
+        GSS_MID_TW(c, w);
+#if GSS_E1_V2
+        const v2* e1v = reinterpret_cast<const v2*>(c.e1) + q * G::P1 + k0;
+        a[0].re = e1v[0]; a[0].im = e1v[G::E1V_PLANE];
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) {
+            cv2 t;
+            t.re = e1v[8 * k1]; t.im = e1v[8 * k1 + G::E1V_PLANE];
+            a[k1] = cmul<true>(t, w[k1]);
+        }
+#else
         const float* re0 = c.e1 + (2 * q) * G::P1 + k0;
         const float* re1 = re0 + G::P1;
         a[0].re = make_float2(re0[0], re1[0]);
         a[0].im = make_float2(re0[G::E1_PLANE], re1[G::E1_PLANE]);
-        GSS_MID_TW(c, w);
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) {
             cv2 t;
@@ -366,6 +420,7 @@ __device__ __forceinline__ void fft_inverse(const TeamCtx<N>& c, cv2 (&a)[8], Ho
             t.im = make_float2(re0[8 * k1 + G::E1_PLANE], re1[8 * k1 + G::E1_PLANE]);
             a[k1] = cmul<true>(t, w[k1]);
         }
+#endif
         dft8<true>(a);
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1)
